@@ -1,0 +1,177 @@
+/*
+ * searcharray_b200.h -- C ABI of libsearcharray_b200.so (sm_100a CUDA kernels).
+ *
+ * Drop-in boundary for SearchArray's scoring hot path.  The
+ * reference (softwaredoug/searcharray, paths below relative to its repo root) has no C
+ * ABI of its own: its "operator interface" is a set of Cython `def`s taking host numpy
+ * arrays.  Replacing those one-for-one would bounce every intermediate over PCIe, so
+ * the boundary sits one level up, at what SearchArray.score / .termfreqs call on
+ * `self.posns` and `similarity` (searcharray/postings.py:607-708).
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (text via
+ * sa_last_error(), thread-local).  Host pointers are borrowed for the duration of the
+ * call only.  Plain pointers and sizes -- no torch / numpy types.  A handle may be used
+ * from several host threads (calls on one handle serialise on an internal mutex, the
+ * reference's tests fire .score from 3 threads: test/test_tmdb.py:285-312).
+ *
+ * Posting word layout (searcharray/roaringish/roaringish.py:30-35):
+ *     bits 63..36 doc id (28 b) | 35..18 block = posn / 18 (18 b) | 17..0 bitmap of posn % 18
+ * Words of one term are sorted ascending and header-unique (header = bits 63..18).
+ */
+#ifndef SEARCHARRAY_B200_H
+#define SEARCHARRAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sa_index sa_index;
+
+#define SA_OK 0
+#define SA_ERR_CUDA 1
+#define SA_ERR_ARG 2
+#define SA_ERR_NOMEM 3
+#define SA_ERR_NCCL 4
+
+#define SA_NO_TERM 0xFFFFFFFFu      /* "token not in the term dictionary" (TermMissingError) */
+#define SA_NO_DOC 0xFFFFFFFFu       /* empty top-k slot */
+#define SA_MAX_PHRASE_TERMS 16
+#define SA_ALL_BITS 0xFFFFFFFFFFFFFFFFull
+
+/* ----------------------------------------------------------------------- misc */
+const char *sa_last_error(void);
+int sa_device_count(int *n_out);
+/* Pinned host memory for result vectors (D2H of a dense float32[N] at full PCIe rate). */
+int sa_host_alloc(void **ptr_out, uint64_t bytes);
+int sa_host_free(void *ptr);
+
+/* ---------------------------------------------------------------------- index
+ * Uploads one shard of the inverted index into HBM.  Replaces the host-side state the
+ * hot path reads: ArrayDict.data / .metadata (searcharray/phrase/memmap_arrays.py:15-53),
+ * SearchArray.doc_lens (postings.py:293-299) and the docfreq cache
+ * (searcharray/phrase/middle_out.py:511-528, warm() :337-342: per-term df is computed on
+ * the device at upload).
+ *   words        all terms' posting words, concatenated          [n_words]
+ *   term_offsets / term_lengths   slice of `words` per term id    [n_terms]
+ *   doc_lens     float32 length of every doc in the shard         [n_docs]
+ *   doc_base     global id of the shard's first doc; the shard owns [doc_base, doc_base+n_docs)
+ *                and every word's doc id must lie in that range (doc-range sharding, sec. 8e)
+ */
+int sa_index_create(const uint64_t *words, uint64_t n_words,
+                    const uint64_t *term_offsets, const uint64_t *term_lengths, uint32_t n_terms,
+                    const float *doc_lens, uint64_t n_docs, uint64_t doc_base,
+                    int device, sa_index **index_out);
+int sa_index_destroy(sa_index *index);
+int sa_index_info(const sa_index *index, uint64_t *n_docs, uint64_t *n_words,
+                  uint32_t *n_terms, uint64_t *device_bytes);
+
+/* PosnBitArray.docfreq (middle_out.py:521-528): distinct docs of the term in this shard. */
+int sa_docfreq(sa_index *index, uint32_t term_id, uint64_t *df_out);
+
+/* Restricts subsequent queries to a subset of the shard's docs -- the sliced-array
+ * semantics of SearchArray.__getitem__ / FilteredPosns (postings.py:344-358,
+ * middle_out.py:291-317).  `rows` = sorted local doc indices (0-based in the shard);
+ * results then have n_rows entries, in `rows` order.  rows == NULL clears the filter. */
+int sa_index_set_rows(sa_index *index, const uint64_t *rows, uint64_t n_rows);
+/* docfreq on the filtered postings (reference quirk iii: df is taken on the slice). */
+int sa_docfreq_rows(sa_index *index, uint32_t term_id, uint64_t *df_out);
+
+/* ------------------------------------------------------------------ term path
+ * SearchArray.termfreqs(token) (postings.py:607-638): popcount64_reduce + as_dense fused;
+ * out = float32[n_docs] on the host (or [n_rows] when a row filter is set).
+ * min_payload/max_payload: RoaringishEncoder.slice's block filter exactly as the reference
+ * applies it (roaringish.py:267-282 + roaringish_ops.pyx:46-68: compares the UNSHIFTED
+ * masked word with min_posn/18 and max_posn/18); pass 0 and SA_ALL_BITS for "no filter". */
+int sa_termfreqs(sa_index *index, uint32_t term_id,
+                 uint64_t min_payload, uint64_t max_payload, float *out_host);
+
+/* SearchArray.score(token, similarity=bm25_similarity(k1, b)) (postings.py:652-680 +
+ * similarity.py:24-38 + bm25/bm25.pyx:11-41): termfreqs + BM25 fused in one kernel.
+ * idf is computed by the host exactly as compute_idf does (similarity.py:19-21, float64 ->
+ * C float); avg_doc_len, k1, b as the reference passes them to bm25_score. */
+int sa_score_term(sa_index *index, uint32_t term_id, float idf, float avg_doc_len,
+                  float k1, float b, uint64_t min_payload, uint64_t max_payload,
+                  float *out_host);
+
+/* ---------------------------------------------------------------- phrase path
+ * SearchArray._phrase_freq / PosnBitArray.phrase_freqs (postings.py:689-708,
+ * middle_out.py:418-446): slop == 0 -> compute_phrase_freqs (middle-out bigram chain,
+ * phrase/bigram_freqs.py); slop > 0 -> span_search (phrase/spans.py, roaringish/spans.pyx).
+ * Any term id == SA_NO_TERM -> zeros.  n_terms >= 2. */
+int sa_phrase_freqs(sa_index *index, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
+                    uint64_t min_payload, uint64_t max_payload, float *out_host);
+int sa_score_phrase(sa_index *index, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
+                    float idf, float avg_doc_len, float k1, float b,
+                    uint64_t min_payload, uint64_t max_payload, float *out_host);
+
+/* ------------------------------------------------------- batched, HBM-resident
+ * The queries/sec path: scores stay in HBM, only the top-k leaves the device.
+ * Query q = terms[term_starts[q] .. term_starts[q+1]) (1 term = BM25 term query, >= 2 =
+ * phrase with `slop`), idf[q] as above.  For every query the dense float32[n_docs] score
+ * vector is produced in HBM exactly as sa_score_term / sa_score_phrase would, then reduced
+ * to the k best (score desc, doc id asc; only score > 0; empty slots = SA_NO_DOC / 0).
+ * out_docs[q*k + i] are GLOBAL doc ids (doc_base added).  The reference idiom this
+ * replaces is np.argpartition(scores, -N) (searcharray/utils/sort.py:24). */
+int sa_score_batch_topk(sa_index *index, const uint32_t *terms, const uint32_t *term_starts,
+                        const float *idf, uint32_t n_queries, uint32_t slop,
+                        float avg_doc_len, float k1, float b, uint32_t k,
+                        uint32_t *out_docs, float *out_scores);
+
+/* Kernel-time accounting for roofline reporting (CUDA events on the library's stream):
+ * milliseconds spent in, and launches of, the dominant kernels since the last reset. */
+typedef struct {
+    double term_kernel_ms;
+    uint64_t term_kernel_launches;
+    uint64_t term_kernel_queries;     /* queries covered by those launches */
+    double topk_kernel_ms;
+    uint64_t topk_kernel_launches;
+    double phrase_kernel_ms;
+    uint64_t phrase_kernel_launches;
+    uint64_t total_launches;          /* every kernel launched by the library */
+} sa_stats;
+int sa_stats_reset(sa_index *index);
+int sa_stats_get(sa_index *index, sa_stats *out);
+int sa_set_profiling(sa_index *index, int enabled);   /* per-kernel CUDA events on/off */
+
+/* -------------------------------------------------------------- multi-GPU (8e)
+ * One process per GPU, each owning a contiguous doc-id range.  The only exchange on the
+ * scoring path is one all-gather of per-shard top-k per query batch.
+ * sa_comm_unique_id fills a 128-byte NCCL unique id on rank 0 (the caller broadcasts it
+ * with whatever bootstrap it has); sa_comm_init joins the clique. */
+int sa_comm_unique_id(void *id128_out);
+int sa_comm_init(sa_index *index, const void *id128, int rank, int world_size);
+int sa_comm_destroy(sa_index *index);
+/* Harness plumbing over the same communicator: barrier, and max-over-ranks of a double
+ * (bench.py uses these for the barrier + max-over-ranks timing rule). */
+int sa_comm_barrier(sa_index *index);
+int sa_comm_allreduce_max(sa_index *index, double *inout);
+/* Like sa_score_batch_topk on every rank's shard, then ncclAllGather of the per-shard
+ * (doc, score) lists and a k-way merge on the device; every rank receives the global top-k. */
+int sa_score_batch_topk_allgather(sa_index *index, const uint32_t *terms, const uint32_t *term_starts,
+                                  const float *idf, uint32_t n_queries, uint32_t slop,
+                                  float avg_doc_len, float k1, float b, uint32_t k,
+                                  uint32_t *out_docs, float *out_scores);
+
+/* ------------------------------------------------- per-op exports (parity tests)
+ * Device implementations of the reference's native ops on raw arrays (host in, host out),
+ * for kernel-level parity tests against the Cython originals. */
+/* popcount64_reduce (roaringish/popcount.pyx:212-237): returns groups in *n_out */
+int sa_op_popcount64_reduce(const uint64_t *words, uint64_t n, int device,
+                            uint64_t *keys_out, float *counts_out, uint64_t *n_out);
+/* bm25_score (bm25/bm25.pyx:28-41): in place over all n */
+int sa_op_bm25_score(float *tf_inout, const float *doc_lens, uint64_t n, float avg_doc_len,
+                     float idf, float k1, float b, int device);
+/* bigram_freqs (phrase/bigram_freqs.py:213-307): cont_rhs=1 -> Continuation.RHS else LHS.
+ * ids/counts: per-doc matches (zero-count docs kept, quirk iv); next: continuation words.
+ * Capacities: ids/counts >= min(n_lhs,n_rhs)*2, next >= 2*min(n_lhs, n_rhs)+2. */
+int sa_op_bigram_freqs(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                       int cont_rhs, int device,
+                       uint64_t *ids_out, float *counts_out, uint64_t *n_ids_out,
+                       uint64_t *next_out, uint64_t *n_next_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEARCHARRAY_B200_H */

@@ -1,0 +1,96 @@
+// sa_comm.cu -- the one collective on the scoring path: every rank
+// owns a contiguous doc-id range, scores its shard, and the per-shard top-k lists are
+// exchanged with a single ncclAllGather per query batch, then merged on the device.
+#include <nccl.h>
+
+#include "sa_term.cuh"
+
+#define SA_NCCL(call)                                                                  \
+    do {                                                                               \
+        ncclResult_t r_ = (call);                                                      \
+        if (r_ != ncclSuccess) {                                                       \
+            sa_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+            return SA_ERR_NCCL;                                                        \
+        }                                                                              \
+    } while (0)
+
+extern "C" int sa_comm_unique_id(void *id128_out) {
+    SA_CHECK(id128_out, "id buffer is NULL");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    SA_NCCL(ncclGetUniqueId(&id));
+    memcpy(id128_out, &id, sizeof(id));
+    return SA_OK;
+}
+
+extern "C" int sa_comm_init(sa_index *ix, const void *id128, int rank, int world_size) {
+    SA_CHECK(ix && id128, "NULL argument");
+    SA_CHECK(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    SA_NCCL(ncclCommInitRank(&comm, world_size, id, rank));
+    ix->nccl_comm = comm;
+    ix->rank = rank;
+    ix->world = world_size;
+    return SA_OK;
+}
+
+extern "C" int sa_comm_destroy(sa_index *ix) {
+    if (ix && ix->nccl_comm) {
+        ncclCommDestroy((ncclComm_t)ix->nccl_comm);
+        ix->nccl_comm = nullptr;
+    }
+    return SA_OK;
+}
+
+extern "C" int sa_comm_barrier(sa_index *ix) {
+    SA_CHECK(ix && ix->nccl_comm, "communicator not initialised");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    int rc = ix->misc.reserve(256);
+    if (rc) return rc;
+    SA_CUDA(cudaMemsetAsync(ix->misc.p, 0, sizeof(float), ix->stream));
+    SA_NCCL(ncclAllReduce(ix->misc.p, ix->misc.p, 1, ncclFloat, ncclSum, (ncclComm_t)ix->nccl_comm, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+extern "C" int sa_comm_allreduce_max(sa_index *ix, double *inout) {
+    SA_CHECK(ix && ix->nccl_comm && inout, "communicator not initialised");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    int rc = ix->misc.reserve(256);
+    if (rc) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->misc.p, inout, sizeof(double), cudaMemcpyHostToDevice, ix->stream));
+    SA_NCCL(ncclAllReduce(ix->misc.p, ix->misc.p, 1, ncclDouble, ncclMax, (ncclComm_t)ix->nccl_comm, ix->stream));
+    SA_CUDA(cudaMemcpyAsync(inout, ix->misc.p, sizeof(double), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+extern "C" int sa_score_batch_topk_allgather(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                                             const float *idf, uint32_t n_queries, uint32_t slop,
+                                             float avg_doc_len, float k1, float b, uint32_t k,
+                                             uint32_t *out_docs, float *out_scores) {
+    SA_CHECK(ix && out_docs && out_scores, "NULL argument");
+    SA_CHECK(ix->nccl_comm, "communicator not initialised (sa_comm_init)");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = sa_batch_topk_device(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
+    if (rc) return rc;
+    const size_t nk = (size_t)n_queries * k;
+    if (nk == 0) return SA_OK;
+    // [world][Q][k] gathered keys, then [Q][k] merged
+    if ((rc = ix->gather.reserve(((size_t)ix->world + 1) * nk * sizeof(u64)))) return rc;
+    u64 *d_all = ix->gather.as<u64>();
+    u64 *d_merged = d_all + (size_t)ix->world * nk;
+    SA_NCCL(ncclAllGather(ix->topk_out.p, d_all, nk, ncclUint64, (ncclComm_t)ix->nccl_comm, ix->stream));
+    if ((rc = launch_topk_merge(ix, d_all, (u32)ix->world, n_queries, k, d_merged))) return rc;
+    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_merged, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    return SA_OK;
+}

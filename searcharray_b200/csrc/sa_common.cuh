@@ -1,0 +1,197 @@
+// sa_common.cuh -- shared definitions for libsearcharray_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/searcharray_b200.h"
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int64_t i64;
+
+// ---- roaringish bit layout (reference searcharray/roaringish/roaringish.py:30-35) ----
+#define SA_KEY_SHIFT 36
+#define SA_LSB_BITS 18
+#define SA_LSB_MASK 0x3FFFFull
+#define SA_HDR_MASK 0xFFFFFFFFFFFC0000ull
+#define SA_MSB_MASK 0x0000000FFFFC0000ull
+#define SA_BIT17 (1ull << 17)
+#define SA_ONE_BLOCK (1ull << SA_LSB_BITS)
+
+#define SA_NUM_SMS_FALLBACK 148
+
+// ---- error plumbing -------------------------------------------------------------
+void sa_set_error(const char *fmt, ...);
+
+#define SA_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            sa_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return SA_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+#define SA_CHECK(cond, ...)                                                            \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            sa_set_error(__VA_ARGS__);                                                 \
+            return SA_ERR_ARG;                                                         \
+        }                                                                              \
+    } while (0)
+
+// ---- a growable device buffer -----------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return SA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            sa_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            p = nullptr;
+            return SA_ERR_NOMEM;
+        }
+        cap = want;
+        return SA_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+// ---- BM25 parameters as the reference passes them to bm25_score ---------------------
+struct Bm25Params {
+    float idf, avg_doc_len, k1, b, one_minus_b;
+    // 1 when a doc with tf == 0 provably scores +0.0f (k1>0, 0<=b<1, finite idf>=+0,
+    // doc_lens >= 0, avgdl > 0): the kernel then only touches doc_lens of matching docs.
+    // 0 -> the formula is evaluated for every doc like bm25.pyx:20-25 does (NaN/inf/-0.0
+    // cases included).
+    int sparse_ok;
+};
+
+// A query against one shard, as the kernels see it.
+struct TermQuery {
+    u64 word_off;      // offset of the term's first word in d_words
+    u64 n_words;       // 0 => unknown term (zeros)
+    float idf;
+};
+
+// ---- the index handle ---------------------------------------------------------------
+struct sa_index {
+    int device = 0;
+    int num_sms = SA_NUM_SMS_FALLBACK;
+    u64 n_docs = 0, n_words = 0, doc_base = 0;
+    u32 n_terms = 0;
+    bool doc_lens_nonneg = true;
+
+    // HBM-resident index
+    u64 *d_words = nullptr;          // [n_words + 1] (one readable pad word)
+    float *d_doc_lens = nullptr;     // [n_docs]
+    u32 *d_df = nullptr;             // [n_terms] distinct docs per term (this shard)
+    // host mirrors for query set-up
+    std::vector<u64> h_off, h_len;
+    std::vector<u32> h_df;
+
+    // sliced-array filter (FilteredPosns semantics)
+    u64 n_rows = 0;                  // 0 => no filter
+    u64 *d_rows = nullptr;           // sorted local doc indices
+    unsigned char *d_row_mask = nullptr;  // [n_docs] 1 if doc selected
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profiling = false;
+    sa_stats stats;
+    std::mutex mu;
+
+    // scratch
+    DevBuf dense;        // float [chunk][n_docs_padded]
+    DevBuf queries;      // TermQuery[] / phrase descriptors
+    DevBuf cand;         // top-k candidates
+    DevBuf cand_meta;    // per-query counters / thresholds
+    DevBuf topk_out;     // per-query (doc, score) results
+    DevBuf phrase_scratch;
+    DevBuf misc;
+    void *h_pinned = nullptr;   // pinned staging
+    size_t h_pinned_cap = 0;
+
+    // NCCL
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    DevBuf gather;
+
+    size_t device_bytes = 0;
+};
+
+int sa_pinned_reserve(sa_index *ix, size_t bytes);
+
+// kernel timing helper: records events around a launch sequence when profiling is on
+struct KernelTimer {
+    sa_index *ix;
+    double *acc_ms;
+    bool on;
+    KernelTimer(sa_index *ix_, double *acc) : ix(ix_), acc_ms(acc), on(ix_->profiling) {
+        if (on) cudaEventRecord(ix->ev0, ix->stream);
+    }
+    void stop() {
+        if (!on) return;
+        cudaEventRecord(ix->ev1, ix->stream);
+        cudaEventSynchronize(ix->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ix->ev0, ix->ev1);
+        *acc_ms += ms;
+        on = false;
+    }
+};
+
+// ---- device helpers -------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// BM25 exactly as bm25.pyx:20-25 evaluates it on x86-64 without FMA contraction:
+// every operation individually rounded to nearest-even float32.
+__device__ __forceinline__ float bm25_one(float tf, float dl, const Bm25Params &p) {
+    float ratio = __fdiv_rn(dl, p.avg_doc_len);
+    float norm = __fmul_rn(p.k1, __fadd_rn(p.one_minus_b, __fmul_rn(p.b, ratio)));
+    return __fmul_rn(__fdiv_rn(tf, __fadd_rn(tf, norm)), p.idf);
+}
+
+// Warp-cooperative lower bound: first index i in [lo, hi) with (a[i] >> shift) >= key,
+// 32-ary search (each round probes 32 evenly spaced elements, ballot picks the bucket).
+// All lanes must call; all lanes get the result.
+__device__ __forceinline__ u64 warp_lower_bound_shifted(const u64 *__restrict__ a, u64 lo, u64 hi,
+                                                        u64 key, int shift) {
+    const unsigned lane = threadIdx.x & 31;
+    while (hi - lo > 32) {
+        u64 step = (hi - lo + 31) >> 5;          // ceil(len/32) >= 2
+        u64 probe = lo + (u64)(lane + 1) * step - 1;   // last element of bucket `lane`
+        bool below = (probe < hi) && ((__ldg(a + probe) >> shift) < key);
+        unsigned m = __ballot_sync(0xffffffffu, below);
+        int c = __popc(m);                        // buckets entirely below key (monotone)
+        lo = lo + (u64)c * step;
+        u64 nhi = lo + step;
+        hi = nhi < hi ? nhi : hi;
+        if (lo > hi) lo = hi;
+    }
+    u64 idx = lo + lane;
+    bool below = (idx < hi) && ((__ldg(a + idx) >> shift) < key);
+    unsigned m = __ballot_sync(0xffffffffu, below);
+    return lo + (u64)__popc(m);
+}
+#endif

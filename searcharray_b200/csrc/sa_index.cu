@@ -1,0 +1,430 @@
+// sa_index.cu -- index upload into HBM, per-term document frequencies, and the C-ABI entry
+// points of the term path (see include/searcharray_b200.h for the reference mapping).
+#include <stdarg.h>
+#include <algorithm>
+#include <cmath>
+
+#include "sa_term.cuh"
+
+// ------------------------------------------------------------------ error text
+static thread_local char g_err[1024] = "";
+
+void sa_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *sa_last_error(void) { return g_err; }
+
+extern "C" int sa_device_count(int *n_out) {
+    SA_CHECK(n_out, "n_out is NULL");
+    int n = 0;
+    SA_CUDA(cudaGetDeviceCount(&n));
+    *n_out = n;
+    return SA_OK;
+}
+
+extern "C" int sa_host_alloc(void **ptr_out, uint64_t bytes) {
+    SA_CHECK(ptr_out, "ptr_out is NULL");
+    SA_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SA_OK;
+}
+
+extern "C" int sa_host_free(void *ptr) {
+    if (ptr) SA_CUDA(cudaFreeHost(ptr));
+    return SA_OK;
+}
+
+int sa_pinned_reserve(sa_index *ix, size_t bytes) {
+    if (bytes <= ix->h_pinned_cap) return SA_OK;
+    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
+    ix->h_pinned = nullptr;
+    ix->h_pinned_cap = 0;
+    SA_CUDA(cudaHostAlloc(&ix->h_pinned, bytes, cudaHostAllocDefault));
+    ix->h_pinned_cap = bytes;
+    return SA_OK;
+}
+
+// --------------------------------------------------------------- df at upload
+// docfreq = number of distinct doc ids among a term's words (reference: unique(words >> 36)
+// .size, roaringish/unique.pyx:87-104 via middle_out.py:521-528).  One thread per word; a word
+// is a "doc head" when it starts its term or its doc id differs from its predecessor's.
+__global__ void df_kernel(const u64 *__restrict__ words, u64 n_words,
+                          const u64 *__restrict__ term_off_sorted, const u32 *__restrict__ term_of_slot,
+                          u32 n_slots, u32 *__restrict__ df) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    // slot = last j with term_off_sorted[j] <= i   (slots cover [off, off+len) disjointly)
+    u32 lo = 0, hi = n_slots;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (term_off_sorted[mid] <= i) lo = mid; else hi = mid;
+    }
+    u64 start = term_off_sorted[lo];
+    bool head = (i == start) || ((words[i] >> SA_KEY_SHIFT) != (words[i - 1] >> SA_KEY_SHIFT));
+    if (head) atomicAdd(&df[term_of_slot[lo]], 1u);
+}
+
+extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
+                               const uint64_t *term_offsets, const uint64_t *term_lengths, uint32_t n_terms,
+                               const float *doc_lens, uint64_t n_docs, uint64_t doc_base,
+                               int device, sa_index **index_out) {
+    SA_CHECK(index_out, "index_out is NULL");
+    SA_CHECK(n_words == 0 || words, "words is NULL");
+    SA_CHECK(n_terms == 0 || (term_offsets && term_lengths), "term tables are NULL");
+    SA_CHECK(n_docs == 0 || doc_lens, "doc_lens is NULL");
+    SA_CHECK(doc_base + n_docs <= (1ull << 28), "doc ids exceed the 28-bit key space");
+    for (u32 t = 0; t < n_terms; t++)
+        SA_CHECK(term_offsets[t] + term_lengths[t] <= n_words, "term %u slice out of range", t);
+    SA_CUDA(cudaSetDevice(device));
+
+    sa_index *ix = new sa_index();
+    ix->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ix->num_sms = prop.multiProcessorCount;
+    ix->n_docs = n_docs;
+    ix->n_words = n_words;
+    ix->n_terms = n_terms;
+    ix->doc_base = doc_base;
+    memset(&ix->stats, 0, sizeof(ix->stats));
+    ix->h_off.assign(term_offsets, term_offsets + n_terms);
+    ix->h_len.assign(term_lengths, term_lengths + n_terms);
+    ix->h_df.assign(n_terms, 0);
+
+#define CREATE_CUDA(call)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            sa_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            sa_index_destroy(ix);                                                      \
+            return SA_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&ix->ev0));
+    CREATE_CUDA(cudaEventCreate(&ix->ev1));
+    CREATE_CUDA(cudaMalloc(&ix->d_words, (n_words + 1) * sizeof(u64)));
+    CREATE_CUDA(cudaMemsetAsync(ix->d_words + n_words, 0, sizeof(u64), ix->stream));
+    if (n_words)
+        CREATE_CUDA(cudaMemcpyAsync(ix->d_words, words, n_words * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+    CREATE_CUDA(cudaMalloc(&ix->d_doc_lens, (n_docs + 1) * sizeof(float)));
+    if (n_docs)
+        CREATE_CUDA(cudaMemcpyAsync(ix->d_doc_lens, doc_lens, n_docs * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    CREATE_CUDA(cudaMalloc(&ix->d_df, (size_t)(n_terms + 1) * sizeof(u32)));
+    CREATE_CUDA(cudaMemsetAsync(ix->d_df, 0, (size_t)(n_terms + 1) * sizeof(u32), ix->stream));
+    ix->device_bytes = (n_words + 1) * sizeof(u64) + (n_docs + 1) * sizeof(float) + (size_t)(n_terms + 1) * 4;
+
+    ix->doc_lens_nonneg = true;
+    for (u64 i = 0; i < n_docs; i++)
+        if (!(doc_lens[i] >= 0.0f)) { ix->doc_lens_nonneg = false; break; }
+
+    // df per term on the device
+    if (n_words && n_terms) {
+        std::vector<u32> order;
+        order.reserve(n_terms);
+        for (u32 t = 0; t < n_terms; t++) if (term_lengths[t]) order.push_back(t);
+        std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return term_offsets[a] < term_offsets[b]; });
+        // slices must be disjoint for the head test to be per-term; also cover gaps
+        std::vector<u64> off_sorted;
+        std::vector<u32> term_of_slot;
+        u64 covered = 0;
+        bool full_cover = true;
+        for (u32 t : order) {
+            if (term_offsets[t] != covered) { full_cover = false; break; }
+            off_sorted.push_back(term_offsets[t]);
+            term_of_slot.push_back(t);
+            covered += term_lengths[t];
+        }
+        if (!full_cover || covered != n_words) {
+            sa_set_error("term slices must tile `words` exactly (ArrayDict.compact layout)");
+            sa_index_destroy(ix);
+            return SA_ERR_ARG;
+        }
+        u64 *d_off = nullptr;
+        u32 *d_slot = nullptr;
+        u32 n_slots = (u32)off_sorted.size();
+        CREATE_CUDA(cudaMalloc(&d_off, n_slots * sizeof(u64)));
+        CREATE_CUDA(cudaMalloc(&d_slot, n_slots * sizeof(u32)));
+        CREATE_CUDA(cudaMemcpyAsync(d_off, off_sorted.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+        CREATE_CUDA(cudaMemcpyAsync(d_slot, term_of_slot.data(), n_slots * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+        unsigned blocks = (unsigned)((n_words + 255) / 256);
+        df_kernel<<<blocks, 256, 0, ix->stream>>>(ix->d_words, n_words, d_off, d_slot, n_slots, ix->d_df);
+        CREATE_CUDA(cudaGetLastError());
+        ix->stats.total_launches++;
+        CREATE_CUDA(cudaMemcpyAsync(ix->h_df.data(), ix->d_df, n_terms * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
+        CREATE_CUDA(cudaStreamSynchronize(ix->stream));
+        cudaFree(d_off);
+        cudaFree(d_slot);
+    } else {
+        CREATE_CUDA(cudaStreamSynchronize(ix->stream));
+    }
+#undef CREATE_CUDA
+    *index_out = ix;
+    return SA_OK;
+}
+
+extern "C" int sa_index_destroy(sa_index *ix) {
+    if (!ix) return SA_OK;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    sa_comm_destroy(ix);
+    cudaFree(ix->d_words);
+    cudaFree(ix->d_doc_lens);
+    cudaFree(ix->d_df);
+    cudaFree(ix->d_rows);
+    cudaFree(ix->d_row_mask);
+    ix->dense.release();
+    ix->queries.release();
+    ix->cand.release();
+    ix->cand_meta.release();
+    ix->topk_out.release();
+    ix->phrase_scratch.release();
+    ix->misc.release();
+    ix->gather.release();
+    if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
+    if (ix->ev0) cudaEventDestroy(ix->ev0);
+    if (ix->ev1) cudaEventDestroy(ix->ev1);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return SA_OK;
+}
+
+extern "C" int sa_index_info(const sa_index *ix, uint64_t *n_docs, uint64_t *n_words,
+                             uint32_t *n_terms, uint64_t *device_bytes) {
+    SA_CHECK(ix, "index is NULL");
+    if (n_docs) *n_docs = ix->n_docs;
+    if (n_words) *n_words = ix->n_words;
+    if (n_terms) *n_terms = ix->n_terms;
+    if (device_bytes) *device_bytes = ix->device_bytes;
+    return SA_OK;
+}
+
+extern "C" int sa_docfreq(sa_index *ix, uint32_t term_id, uint64_t *df_out) {
+    SA_CHECK(ix && df_out, "NULL argument");
+    if (term_id == SA_NO_TERM) { *df_out = 0; return SA_OK; }
+    SA_CHECK(term_id < ix->n_terms, "term id %u out of range", term_id);
+    *df_out = ix->h_df[term_id];
+    return SA_OK;
+}
+
+extern "C" int sa_stats_reset(sa_index *ix) {
+    SA_CHECK(ix, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    memset(&ix->stats, 0, sizeof(ix->stats));
+    return SA_OK;
+}
+
+extern "C" int sa_stats_get(sa_index *ix, sa_stats *out) {
+    SA_CHECK(ix && out, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    *out = ix->stats;
+    return SA_OK;
+}
+
+extern "C" int sa_set_profiling(sa_index *ix, int enabled) {
+    SA_CHECK(ix, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->profiling = enabled != 0;
+    return SA_OK;
+}
+
+// ----------------------------------------------------------------- term path
+static Bm25Params make_bm25(const sa_index *ix, float idf, float avg_doc_len, float k1, float b) {
+    Bm25Params p;
+    p.idf = idf;
+    p.avg_doc_len = avg_doc_len;
+    p.k1 = k1;
+    p.b = b;
+    p.one_minus_b = 1 - b;       // float arithmetic, as `cdef float one_minus_b = 1 - b` (bm25.pyx:19)
+    p.sparse_ok = (ix->doc_lens_nonneg && k1 > 0.0f && std::isfinite(k1) && b >= 0.0f && b < 1.0f &&
+                   avg_doc_len > 0.0f && std::isfinite(avg_doc_len) && std::isfinite(idf) &&
+                   idf >= 0.0f && !std::signbit(idf)) ? 1 : 0;
+    return p;
+}
+
+static u64 padded_docs(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
+
+static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Params &p,
+                       u64 min_payload, u64 max_payload, float *out_host) {
+    SA_CHECK(ix && out_host, "NULL argument");
+    SA_CHECK(term_id == SA_NO_TERM || term_id < ix->n_terms, "term id %u out of range", term_id);
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    if (ix->n_docs == 0) return SA_OK;
+    const u64 stride = padded_docs(ix->n_docs);
+    int rc = ix->dense.reserve(stride * sizeof(float));
+    if (rc) return rc;
+    rc = ix->queries.reserve(sizeof(TermQuery));
+    if (rc) return rc;
+    TermQuery tq;
+    tq.word_off = term_id == SA_NO_TERM ? 0 : ix->h_off[term_id];
+    tq.n_words = term_id == SA_NO_TERM ? 0 : ix->h_len[term_id];
+    tq.idf = p.idf;
+    SA_CUDA(cudaMemcpyAsync(ix->queries.p, &tq, sizeof(tq), cudaMemcpyHostToDevice, ix->stream));
+    TermBatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.words = ix->d_words;
+    a.doc_lens = ix->d_doc_lens;
+    a.n_docs = ix->n_docs;
+    a.doc_base = ix->doc_base;
+    a.queries = ix->queries.as<TermQuery>();
+    a.out = ix->dense.as<float>();
+    a.out_stride = stride;
+    a.bm25 = p;
+    a.min_payload = min_payload;
+    a.max_payload = max_payload;
+    a.filter = !(min_payload == 0 && max_payload == SA_ALL_BITS);
+    a.mode = mode;
+    a.topk.k = 0;
+    rc = launch_term_batch(ix, a, 1);
+    if (rc) return rc;
+    SA_CUDA(cudaMemcpyAsync(out_host, ix->dense.p, ix->n_docs * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+extern "C" int sa_termfreqs(sa_index *ix, uint32_t term_id, uint64_t min_payload, uint64_t max_payload,
+                            float *out_host) {
+    SA_CHECK(ix, "index is NULL");
+    Bm25Params p = make_bm25(ix, 0, 1, 1, 0);
+    return single_term(ix, term_id, TERM_MODE_TF, p, min_payload, max_payload, out_host);
+}
+
+extern "C" int sa_score_term(sa_index *ix, uint32_t term_id, float idf, float avg_doc_len,
+                             float k1, float b, uint64_t min_payload, uint64_t max_payload,
+                             float *out_host) {
+    SA_CHECK(ix, "index is NULL");
+    if (avg_doc_len == 0.0f) {   // similarity.py:31-32: zeros_like(term_freqs)
+        SA_CHECK(out_host, "out is NULL");
+        memset(out_host, 0, ix->n_docs * sizeof(float));
+        return SA_OK;
+    }
+    Bm25Params p = make_bm25(ix, idf, avg_doc_len, k1, b);
+    return single_term(ix, term_id, TERM_MODE_SCORE, p, min_payload, max_payload, out_host);
+}
+
+// ------------------------------------------------ batched, HBM-resident top-k
+// One chunk: score Q queries into ix->dense, collect candidates, select top-k into d_keys.
+static int run_topk_chunk(sa_index *ix, const std::vector<TermQuery> &qs, const Bm25Params &p,
+                          u32 k, u32 cap, u64 *d_keys) {
+    const u32 Q = (u32)qs.size();
+    const u64 stride = padded_docs(ix->n_docs);
+    int rc;
+    if ((rc = ix->dense.reserve((size_t)Q * stride * sizeof(float)))) return rc;
+    if ((rc = ix->queries.reserve((size_t)Q * sizeof(TermQuery)))) return rc;
+    if ((rc = ix->cand.reserve((size_t)Q * cap * sizeof(u64)))) return rc;
+    if ((rc = ix->cand_meta.reserve((size_t)Q * 2 * sizeof(u32)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->queries.p, qs.data(), (size_t)Q * sizeof(TermQuery), cudaMemcpyHostToDevice, ix->stream));
+    SA_CUDA(cudaMemsetAsync(ix->cand_meta.p, 0, (size_t)Q * 2 * sizeof(u32), ix->stream));
+    TermBatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.words = ix->d_words;
+    a.doc_lens = ix->d_doc_lens;
+    a.n_docs = ix->n_docs;
+    a.doc_base = ix->doc_base;
+    a.queries = ix->queries.as<TermQuery>();
+    a.out = ix->dense.as<float>();
+    a.out_stride = stride;
+    a.bm25 = p;
+    a.min_payload = 0;
+    a.max_payload = SA_ALL_BITS;
+    a.filter = 0;
+    a.mode = TERM_MODE_SCORE;
+    a.topk.thr_bits = ix->cand_meta.as<u32>();
+    a.topk.count = ix->cand_meta.as<u32>() + Q;
+    a.topk.cand = ix->cand.as<u64>();
+    a.topk.cap = cap;
+    a.topk.k = k;
+    if ((rc = launch_term_batch(ix, a, Q))) return rc;
+    if ((rc = launch_topk_select(ix, a.topk, Q, ix->doc_base, d_keys))) return rc;
+    // candidate counts back to the host (overflow check)
+    if ((rc = sa_pinned_reserve(ix, std::max<size_t>((size_t)Q * sizeof(u32), 4096)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, a.topk.count, (size_t)Q * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
+    TermQuery tq;
+    tq.word_off = t == SA_NO_TERM ? 0 : ix->h_off[t];
+    tq.n_words = t == SA_NO_TERM ? 0 : ix->h_len[t];
+    tq.idf = idf;
+    return tq;
+}
+
+int sa_batch_topk_device(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                         const float *idf, uint32_t n_queries, uint32_t slop,
+                         float avg_doc_len, float k1, float b, uint32_t k) {
+    (void)slop;
+    SA_CHECK(ix && terms && term_starts && idf, "NULL argument");
+    SA_CHECK(k >= 1 && k <= SA_TOPK_MAX, "k must be in [1, %d]", SA_TOPK_MAX);
+    SA_CUDA(cudaSetDevice(ix->device));
+    int rc;
+    if ((rc = ix->topk_out.reserve(std::max<size_t>((size_t)n_queries * k * sizeof(u64), 256)))) return rc;
+    u64 *d_keys = ix->topk_out.as<u64>();
+    SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)n_queries * k * sizeof(u64), ix->stream));
+    if (ix->n_docs == 0 || n_queries == 0 || avg_doc_len == 0.0f) return SA_OK;
+    const u64 stride = padded_docs(ix->n_docs);
+    // chunk so the dense score vectors of one chunk stay within ~4 GB of HBM
+    u32 chunk = (u32)std::max<u64>(1, std::min<u64>(n_queries, (4ull << 30) / (stride * sizeof(float))));
+    chunk = std::min<u32>(chunk, 65535);
+    const u32 cap = (u32)std::min<u64>(ix->n_docs, 1u << 16);
+    std::vector<TermQuery> qs;
+    std::vector<u32> redo;
+    for (u32 q0 = 0; q0 < n_queries; q0 += chunk) {
+        const u32 Q = std::min(chunk, n_queries - q0);
+        qs.clear();
+        Bm25Params p = make_bm25(ix, 1.0f, avg_doc_len, k1, b);
+        for (u32 q = q0; q < q0 + Q; q++) {
+            SA_CHECK(term_starts[q + 1] - term_starts[q] == 1,
+                     "query %u: phrase queries in a batch are not supported yet", q);
+            u32 t = terms[term_starts[q]];
+            SA_CHECK(t == SA_NO_TERM || t < ix->n_terms, "term id %u out of range", t);
+            qs.push_back(make_term_query(ix, t, idf[q]));
+            // sparse_ok must hold for every idf in the chunk
+            if (!make_bm25(ix, idf[q], avg_doc_len, k1, b).sparse_ok) p.sparse_ok = 0;
+        }
+        if ((rc = run_topk_chunk(ix, qs, p, k, cap, d_keys + (u64)q0 * k))) return rc;
+        const u32 *counts = (const u32 *)ix->h_pinned;
+        for (u32 q = 0; q < Q; q++) if (counts[q] > cap) redo.push_back(q0 + q);
+    }
+    // candidate overflow (threshold rose too slowly, e.g. scores ascending with doc id or
+    // massive ties): re-run those queries one at a time with room for every doc.
+    for (u32 q : redo) {
+        qs.clear();
+        qs.push_back(make_term_query(ix, terms[term_starts[q]], idf[q]));
+        Bm25Params p = make_bm25(ix, idf[q], avg_doc_len, k1, b);
+        if ((rc = run_topk_chunk(ix, qs, p, k, (u32)ix->n_docs, d_keys + (u64)q * k))) return rc;
+    }
+    return SA_OK;
+}
+
+void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_scores) {
+    for (u64 i = 0; i < n; i++) {
+        u64 key = keys[i];
+        if (key == 0) { out_docs[i] = SA_NO_DOC; out_scores[i] = 0.0f; continue; }
+        out_docs[i] = 0xFFFFFFFFu - (u32)(key & 0xFFFFFFFFull);
+        u32 bits = (u32)(key >> 32);
+        memcpy(&out_scores[i], &bits, 4);
+    }
+}
+
+extern "C" int sa_score_batch_topk(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                                   const float *idf, uint32_t n_queries, uint32_t slop,
+                                   float avg_doc_len, float k1, float b, uint32_t k,
+                                   uint32_t *out_docs, float *out_scores) {
+    SA_CHECK(ix && out_docs && out_scores, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = sa_batch_topk_device(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
+    if (rc) return rc;
+    const size_t nk = (size_t)n_queries * k;
+    if (nk == 0) return SA_OK;
+    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, ix->topk_out.p, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    return SA_OK;
+}

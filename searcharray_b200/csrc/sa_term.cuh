@@ -1,0 +1,42 @@
+// sa_term.cuh -- kernel-side declarations shared by the term-path translation units.
+#pragma once
+#include "sa_common.cuh"
+
+#define SA_TILE_DOCS 4096          // docs per CTA tile (16 KB of float32 scores)
+#define SA_TERM_THREADS 256
+#define SA_TOPK_MAX 32             // warp-level threshold estimation handles k <= 32
+
+enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
+
+// Per-query top-k collection state in HBM (see sa_topk.cu).
+struct TopkCtx {
+    u32 *thr_bits;     // [Q] running lower bound on the k-th best score (float bits; scores >= 0)
+    u32 *count;        // [Q] candidates appended (may exceed cap -> overflow)
+    u64 *cand;         // [Q][cap] key = score_bits << 32 | (0xFFFFFFFF - local_doc)
+    u32 cap;
+    u32 k;             // 0 => no top-k collection
+};
+
+struct TermBatchArgs {
+    const u64 *words;
+    const float *doc_lens;
+    u64 n_docs;
+    u64 doc_base;
+    const TermQuery *queries;   // [Q]
+    float *out;                 // [Q][out_stride]
+    u64 out_stride;             // multiple of SA_TILE_DOCS
+    Bm25Params bm25;            // idf field unused (per query)
+    u64 min_payload, max_payload;
+    int filter;                 // apply the payload_slice filter
+    int mode;
+    TopkCtx topk;
+};
+
+int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries);
+int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys);
+int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
+// Runs the batch on this shard; leaves [n_queries][k] result keys in ix->topk_out (device).
+int sa_batch_topk_device(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                         const float *idf, uint32_t n_queries, uint32_t slop,
+                         float avg_doc_len, float k1, float b, uint32_t k);
+void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_scores);

@@ -1,0 +1,148 @@
+// sa_topk.cu -- exact top-k over the candidates the scoring kernels collected.
+//
+// Replaces the reference idiom np.argpartition(scores, -N)[-N:] (searcharray/utils/sort.py:24)
+// for the HBM-resident batched path.  The scoring kernels append every score that is >= a
+// running, provably-valid lower bound of the k-th best score (sa_term.cu step 4), so the
+// candidate list is a superset of the true top-k and is normally a few hundred entries.
+// Here one CTA per query selects the exact k best by (score desc, doc id asc):
+// candidates <= 4096 -> bitonic sort in shared memory; more -> 8-bit MSB radix select to the
+// k-th key, then sort the survivors.
+#include "sa_term.cuh"
+
+#define SEL_THREADS 512
+#define SEL_SMEM_KEYS 4096
+
+__device__ void bitonic_sort_desc_smem(u64 *s, u32 n_pow2) {
+    for (u32 k = 2; k <= n_pow2; k <<= 1) {
+        for (u32 j = k >> 1; j > 0; j >>= 1) {
+            for (u32 i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                u32 ixj = i ^ j;
+                if (ixj > i) {
+                    u64 a = s[i], b = s[ixj];
+                    bool desc = ((i & k) == 0);
+                    if ((a < b) == desc) { s[i] = b; s[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
+    __shared__ u64 s_keys[SEL_SMEM_KEYS];
+    __shared__ u32 s_hist[256];
+    __shared__ u64 s_prefix;
+    __shared__ u32 s_krem, s_n;
+
+    const u32 q = blockIdx.x;
+    const u32 k = t.k;
+    u32 M = t.count[q];
+    if (M > t.cap) M = t.cap;             // overflow: the host re-runs this query
+    const u64 *__restrict__ keys = t.cand + (u64)q * t.cap;
+    u32 n_valid;                           // number of keys in s_keys
+
+    if (M <= SEL_SMEM_KEYS) {
+        u32 n2 = 1;
+        while (n2 < M) n2 <<= 1;
+        if (n2 < 2) n2 = 2;
+        for (u32 i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < M ? keys[i] : 0ull;
+        __syncthreads();
+        bitonic_sort_desc_smem(s_keys, n2);
+        n_valid = M;
+    } else {
+        // radix select: find the k-th largest key (keys are unique: the doc id is in them)
+        if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
+        __syncthreads();
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            const u64 prefix = s_prefix;
+            for (u32 i = threadIdx.x; i < M; i += blockDim.x) {
+                u64 key = keys[i];
+                bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+                if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                u32 rem = s_krem, acc = 0;
+                int b = 255;
+                for (; b > 0; b--) {
+                    if (acc + s_hist[b] >= rem) break;
+                    acc += s_hist[b];
+                }
+                s_krem = rem - acc;
+                s_prefix = prefix | ((u64)b << shift);
+            }
+            __syncthreads();
+        }
+        const u64 kth = s_prefix;          // exact k-th largest key (M > 4096 >= k)
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < M; i += blockDim.x) {
+            u64 key = keys[i];
+            if (key >= kth) {
+                u32 slot = atomicAdd(&s_n, 1u);
+                if (slot < SEL_SMEM_KEYS) s_keys[slot] = key;
+            }
+        }
+        __syncthreads();
+        n_valid = min(s_n, (u32)SEL_SMEM_KEYS);
+        u32 n2 = 2;
+        while (n2 < n_valid) n2 <<= 1;
+        for (u32 i = n_valid + threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc_smem(s_keys, n2);
+    }
+
+    // result keys carry GLOBAL doc ids: score_bits << 32 | (0xFFFFFFFF - global_doc); 0 = empty
+    for (u32 i = threadIdx.x; i < k; i += blockDim.x) {
+        u64 key = (i < n_valid) ? s_keys[i] : 0ull;
+        if (key != 0ull) key -= doc_base;      // (~local) - base == ~(local + base)
+        out_keys[(u64)q * k + i] = key;
+    }
+}
+
+// Merge per-shard top-k lists after the all-gather: in[r][q][k] -> out[q][k].
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_merge_kernel(const u64 *__restrict__ in, u32 world, u32 n_queries, u32 k, u64 *__restrict__ out) {
+    __shared__ u64 s_keys[SEL_SMEM_KEYS];
+    const u32 q = blockIdx.x;
+    const u32 n = world * k;
+    u32 n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (u32 i = threadIdx.x; i < n2; i += blockDim.x) {
+        u64 v = 0ull;
+        if (i < n) {
+            u32 r = i / k, j = i % k;
+            v = in[((u64)r * n_queries + q) * k + j];
+        }
+        s_keys[i] = v;
+    }
+    __syncthreads();
+    bitonic_sort_desc_smem(s_keys, n2);
+    for (u32 i = threadIdx.x; i < k; i += blockDim.x) out[(u64)q * k + i] = s_keys[i];
+}
+
+int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys) {
+    if (n_queries == 0) return SA_OK;
+    KernelTimer tm(ix, &ix->stats.topk_kernel_ms);
+    topk_select_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(t, doc_base, d_out_keys);
+    SA_CUDA(cudaGetLastError());
+    tm.stop();
+    ix->stats.topk_kernel_launches++;
+    ix->stats.total_launches++;
+    return SA_OK;
+}
+
+int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out) {
+    if (n_queries == 0) return SA_OK;
+    SA_CHECK((u64)world * k <= SEL_SMEM_KEYS, "world*k too large for the merge kernel");
+    KernelTimer tm(ix, &ix->stats.topk_kernel_ms);
+    topk_merge_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(d_in, world, n_queries, k, d_out);
+    SA_CUDA(cudaGetLastError());
+    tm.stop();
+    ix->stats.topk_kernel_launches++;
+    ix->stats.total_launches++;
+    return SA_OK;
+}

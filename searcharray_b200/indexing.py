@@ -1,0 +1,140 @@
+"""Host-side index build (numpy).  Produces the upload format of the GPU index.
+
+Mirrors what the reference builds at index time (searcharray/indexing.py:235-295: tokenize ->
+(term, doc, posn) triples -> stable sort by term -> roaringish encode -> ArrayDict) and the
+state SearchArray.index injects (searcharray/postings.py:293-299): term dictionary, per-term
+posting words, doc_lens, avg_doc_length.  Tokenising is Python-bound and stays on the host
+(out of scope for kernels: SURVEY.md section 2 rows 12-13).
+"""
+import numpy as np
+
+from .roaringish import MAX_POSN, encode_grouped
+
+
+class TermMissingError(KeyError):
+    """reference searcharray/term_dict.py:4-7"""
+
+
+class TermDict:
+    """str <-> id, ids in first-seen order (reference searcharray/term_dict.py:10-59)."""
+
+    def __init__(self):
+        self.term_to_ids = {}
+        self.id_to_terms = []
+
+    def add_term(self, term):
+        tid = self.term_to_ids.get(term)
+        if tid is None:
+            tid = len(self.id_to_terms)
+            self.term_to_ids[term] = tid
+            self.id_to_terms.append(term)
+        return tid
+
+    def get_term_id(self, term):
+        try:
+            return self.term_to_ids[term]
+        except KeyError:
+            raise TermMissingError(f"Term {term} not present in dictionary. Reindex to add.")
+
+    def get_term(self, term_id):
+        try:
+            return self.id_to_terms[term_id]
+        except IndexError:
+            raise TermMissingError(f"Term at {term_id} not present in dictionary. Reindex to add.")
+
+    def __len__(self):
+        return len(self.id_to_terms)
+
+
+class HostIndex:
+    """Flat, upload-ready inverted index: the layout of ArrayDict.data + metadata
+    (reference searcharray/phrase/memmap_arrays.py:15-53) for every term id."""
+
+    def __init__(self, words, term_offsets, term_lengths, doc_lens, term_dict=None, avg_doc_length=None):
+        self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+        self.term_lengths = np.ascontiguousarray(term_lengths, dtype=np.uint64)
+        self.doc_lens = np.ascontiguousarray(doc_lens, dtype=np.float32)
+        self.term_dict = term_dict
+        # np.mean of a float32 array, like reference indexing.py:281
+        if avg_doc_length is None:
+            avg_doc_length = np.mean(self.doc_lens) if len(self.doc_lens) else 0
+        self.avg_doc_length = avg_doc_length
+
+    @property
+    def n_terms(self):
+        return len(self.term_offsets)
+
+    @property
+    def n_docs(self):
+        return len(self.doc_lens)
+
+    def term_words(self, term_id):
+        o, n = int(self.term_offsets[term_id]), int(self.term_lengths[term_id])
+        return self.words[o:o + n]
+
+    def shard(self, doc_lo, doc_hi):
+        """Doc-range shard [doc_lo, doc_hi): every term's sub-list (found by searching the
+        doc-id key, like RoaringishEncoder.key_partition, reference roaringish.py:227-243),
+        doc ids kept absolute."""
+        lo_key, hi_key = np.uint64(doc_lo) << np.uint64(36), np.uint64(doc_hi) << np.uint64(36)
+        parts, offs, lens = [], [], []
+        total = 0
+        for t in range(self.n_terms):
+            w = self.term_words(t)
+            a, b = np.searchsorted(w, lo_key), np.searchsorted(w, hi_key)
+            parts.append(w[a:b])
+            offs.append(total)
+            lens.append(b - a)
+            total += b - a
+        words = np.concatenate(parts) if parts else np.empty(0, dtype=np.uint64)
+        return HostIndex(words, offs, lens, self.doc_lens[doc_lo:doc_hi], self.term_dict, self.avg_doc_length)
+
+
+def build_index(array, tokenizer, truncate=False):
+    """Strings -> HostIndex (reference indexing.py:64-145,235-295 semantics: term ids in
+    first-seen order, position = token index, doc_len = number of tokens)."""
+    term_dict = TermDict()
+    all_terms, all_docs, all_posns = [], [], []
+    doc_lens = np.zeros(len(array), dtype=np.float32)
+    limit = MAX_POSN if truncate else None
+    for doc_id, doc in enumerate(array):
+        toks = tokenizer(doc)
+        ids = np.fromiter((term_dict.add_term(t) for t in toks), dtype=np.int64)[:limit]
+        n = len(ids)
+        doc_lens[doc_id] = n
+        if n:
+            all_terms.append(ids)
+            all_docs.append(np.full(n, doc_id, dtype=np.int64))
+            all_posns.append(np.arange(n, dtype=np.int64))
+    if np.any(doc_lens > MAX_POSN):
+        raise ValueError(f"Document length exceeds maximum of {MAX_POSN}")
+    n_terms = len(term_dict)
+    if all_terms:
+        terms = np.concatenate(all_terms)
+        docs = np.concatenate(all_docs)
+        posns = np.concatenate(all_posns)
+        order = np.argsort(terms, kind="stable")       # docs/posns already ascending
+        words, uniq, offs, lens = encode_grouped(terms[order], docs[order], posns[order])
+    else:
+        words = np.empty(0, dtype=np.uint64)
+        uniq = np.empty(0, dtype=np.int64)
+        offs = lens = np.empty(0, dtype=np.uint64)
+    term_offsets = np.zeros(n_terms, dtype=np.uint64)
+    term_lengths = np.zeros(n_terms, dtype=np.uint64)
+    term_offsets[uniq] = offs
+    term_lengths[uniq] = lens
+    return HostIndex(words, term_offsets, term_lengths, doc_lens, term_dict)
+
+
+def index_from_term_postings(term_names, term_words_list, doc_lens, avg_doc_length=None):
+    """Inject pre-encoded postings (synthetic corpora): one sorted word list per term."""
+    td = TermDict()
+    offs, lens, total = [], [], 0
+    for name, w in zip(term_names, term_words_list):
+        td.add_term(name)
+        offs.append(total)
+        lens.append(len(w))
+        total += len(w)
+    words = np.concatenate(term_words_list) if term_words_list else np.empty(0, dtype=np.uint64)
+    return HostIndex(words, offs, lens, doc_lens, td, avg_doc_length)
