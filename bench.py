@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of SearchArray's scoring hot path on B200 (see BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU reference arm
+
+Workload (config.workload): BASELINE.json configs[1] -- 10M-doc synthetic MSMARCO-shaped corpus
+(searcharray_b200/synth.py, seeded, generated as postings), single-term BM25.  One "step" = one
+pass over a batch of `--queries` stratified single-term queries: every query produces the dense
+float32[N] BM25 score vector in HBM and its exact top-k.  For N > 1 the 10M docs are sharded by
+contiguous doc-id range (strong scaling), one process per GPU, one ncclAllGather of the per-shard
+top-k per batch.
+
+  value : device-resident throughput -- query descriptors already in HBM, CUDA events on the
+          library's stream around exactly K x sa_batch_execute (kernels + all-gather), max over ranks.
+  e2e   : the same batch through the public C-ABI call with HOST buffers per step
+          (sa_score_batch_topk: H2D of the query descriptors, kernels, D2H of the top-k).
+  e2e_dense : the literal `.score()` drop-in (sa_score_term), D2H of the dense float32[N] per query.
+  roofline  : term_tile_kernel, algorithmic bytes 8*W + 4*df + 4*N per query over the
+          kernel's CUDA-event time, against MEASURED_PEAKS.json's hbm_gbs.
+  cpu_baseline : the oracle port (oracle/, the reference's algorithm in C + numpy, warm tf cache)
+          on the host cores, bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K1, B = 1.2, 0.75
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- corpus
+def build_corpus(n_docs, rank, world):
+    from searcharray_b200 import synth
+    spec = synth.SynthSpec(n_docs)
+    t0 = time.time()
+    host, lo, hi = synth.generate_shard(spec, rank, world)
+    # global avg doc length: exact float64 mean over ALL blocks' doc_lens (cheap), as float32
+    total = 0.0
+    for b in range(synth.N_BLOCKS):
+        total += float(np.sum(synth.gen_doc_lens(n_docs, b), dtype=np.float64))
+    avgdl = np.float32(total / n_docs)
+    log(f"rank {rank}: generated docs [{lo},{hi}) {host.words.nbytes / 1e6:.0f} MB of postings "
+        f"in {time.time() - t0:.1f}s, avgdl={avgdl}")
+    return spec, host, lo, hi, avgdl
+
+
+def make_queries(spec, n_queries):
+    from searcharray_b200 import synth
+    names = synth.stratified_term_queries(spec, n_queries)
+    return names, np.asarray([spec.term_index[n] for n in names], dtype=np.uint32)
+
+
+def idf_of(n_docs, df):
+    from searcharray_b200.similarity import compute_idf
+    return np.asarray([compute_idf(n_docs, np.asarray([d])) for d in df], dtype=np.float32)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------- CPU reference arm
+def cpu_reference_runner(host, avgdl, n_docs, k):
+    """The reference's CPU path for this workload, restated by the oracle port: warm tf/df caches
+    (PosnBitArray caches), as_dense + bm25_score over all N docs, np.argpartition top-k."""
+    from oracle import search as osearch
+    idx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
+                              avg_doc_length=avgdl, corpus_size=n_docs, cache=True)
+
+    def one(term_id):
+        scores = idx.score(int(term_id), k1=K1, b=B)
+        top = np.argpartition(scores, -k)[-k:]            # reference utils/sort.py:24
+        return top[np.argsort(-scores[top], kind="stable")]
+    return idx, one
+
+
+def run_cpu_sample(one, term_ids, threads):
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    if threads == 1:
+        for t in term_ids:
+            one(t)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, term_ids))
+    return time.perf_counter() - t0
+
+
+def bench_reference(args, rank, world):
+    if rank != 0:
+        return                                  # rank 0 alone runs the CPU arm
+    spec, host, lo, hi, avgdl = build_corpus(args.docs, 0, 1)
+    names, term_ids = make_queries(spec, args.queries)
+    cores = os.cpu_count() or 1
+    idx, one = cpu_reference_runner(host, avgdl, args.docs, args.k)
+    sample = term_ids[:min(len(term_ids), args.ref_sample)]
+    for t in np.unique(term_ids):               # warm the tf/df caches like SearchArray.warm()
+        idx.docfreq(int(t))
+        idx.termfreqs(int(t))
+    for _ in range(args.warmup):
+        run_cpu_sample(one, sample[:max(8, len(sample) // 8)], cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += run_cpu_sample(one, sample, cores)
+    qps = args.steps * len(sample) / t
+    line = {
+        "impl": "reference", "metric": "queries/sec (single-term BM25 + top-k) on 10M-doc synthetic MSMARCO",
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, len(sample)),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(sample)} of the {args.queries} stratified term queries per step, "
+                                   f"ThreadPool({cores}), warm tf cache"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, queries_per_step):
+    return {"workload": "10M-doc synthetic MSMARCO, single-term BM25, top-%d (BASELINE configs[1])" % args.k,
+            "n_docs": args.docs, "queries_per_step": queries_per_step, "k": args.k,
+            "corpus": "searcharray_b200.synth seed 20260924, doc_lens~clip(lognormal(3.9,.45),8,400), "
+                      "48 query terms over df/N in {3e-1..1e-4}",
+            "sharding": "contiguous doc-id ranges, one process per GPU",
+            "cache": "inputs larger than L2: every step streams queries_per_step dense float32[N] vectors"}
+
+
+# --------------------------------------------------------------------------- our arm
+def bench_ours(args, rank, world):
+    from searcharray_b200 import _lib
+    from searcharray_b200.postings import DeviceIndex
+    L = _lib.lib()
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    spec, host, lo, hi, avgdl = build_corpus(args.docs, rank, world)
+    names, term_ids = make_queries(spec, args.queries)
+    dev = DeviceIndex(host, device=local_rank, doc_base=lo)
+    h = dev.handle
+
+    if world > 1:
+        import torch.distributed as dist         # plumbing only: rendezvous for the NCCL unique id
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        uid = (ctypes.c_char * 128)()
+        if rank == 0:
+            _lib.check(L.sa_comm_unique_id(uid))
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=0)
+        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        _lib.check(L.sa_comm_init(h, uid, rank, world))
+
+    def barrier():
+        if world > 1:
+            _lib.check(L.sa_comm_barrier(h))
+
+    def max_over_ranks(x):
+        v = ctypes.c_double(x)
+        if world > 1:
+            _lib.check(L.sa_comm_allreduce_max(h, ctypes.byref(v)))
+        return v.value
+
+    # global document frequencies (idf must use unsharded df)
+    df = np.zeros(host.n_terms, dtype=np.uint64)
+    tmp = ctypes.c_uint64(0)
+    for t in range(host.n_terms):
+        _lib.check(L.sa_docfreq(h, t, ctypes.byref(tmp)))
+        df[t] = tmp.value
+    if world > 1:
+        _lib.check(L.sa_comm_allreduce_sum_u64(h, _lib.p_u64(df), len(df)))
+    idf = idf_of(args.docs, df[term_ids])
+    starts = np.arange(len(term_ids) + 1, dtype=np.uint32)
+    Q, k = len(term_ids), args.k
+    out_docs = np.empty((Q, k), dtype=np.uint32)
+    out_scores = np.empty((Q, k), dtype=np.float32)
+    n_over = ctypes.c_uint32(0)
+
+    def upload():
+        _lib.check(L.sa_batch_upload(h, _lib.p_u32(term_ids), _lib.p_u32(starts), _lib.p_f32(idf), Q, 0,
+                                     float(avgdl), K1, B, k))
+
+    def execute():
+        _lib.check(L.sa_batch_execute_allgather(h) if world > 1 else L.sa_batch_execute(h))
+
+    def download():
+        if world > 1:
+            _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(out_docs), _lib.p_f32(out_scores),
+                                                     ctypes.byref(n_over)))
+        else:
+            _lib.check(L.sa_batch_download(h, _lib.p_u32(out_docs), _lib.p_f32(out_scores), ctypes.byref(n_over)))
+        return n_over.value
+
+    def e2e_step():
+        upload()
+        execute()
+        return download()
+
+    # ---- warm-up (>= 3 full steps)
+    overflow = 0
+    for _ in range(max(args.warmup, 3)):
+        overflow += e2e_step()
+
+    # ---- value: device-resident, K x execute between CUDA events on the library stream
+    stats = _lib.SaStats()
+    upload()
+    _lib.check(L.sa_stats_reset(h))
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    _lib.check(L.sa_timer_start(h))
+    for _ in range(args.steps):
+        execute()
+    ms = ctypes.c_double(0)
+    _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
+    barrier()
+    dev_ms = max_over_ranks(ms.value)
+    clk = clocks.stop()
+    _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
+    launches_value = int(stats.total_launches)
+    download()
+    value = args.steps * Q / (dev_ms / 1e3)
+
+    # ---- e2e: host buffers in, top-k out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        overflow += e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = args.steps * Q / e2e_s
+    h2d = int(term_ids.nbytes + starts.nbytes + idf.nbytes + Q * 24)     # + TermQuery descriptors
+    d2h = int(Q * k * 8 + Q * 4)
+
+    # ---- roofline of the dominant kernel (per-launch CUDA events, async)
+    W = host.term_lengths[term_ids].astype(np.float64)
+    dfl = np.zeros(host.n_terms, dtype=np.float64)
+    for t in range(host.n_terms):
+        _lib.check(L.sa_docfreq(h, t, ctypes.byref(tmp)))
+        dfl[t] = tmp.value
+    alg_bytes_step = float(np.sum(8.0 * W + 4.0 * dfl[term_ids] + 4.0 * host.n_docs))
+    _lib.check(L.sa_set_profiling(h, 1))
+    _lib.check(L.sa_stats_reset(h))
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        execute()
+    _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
+    _lib.check(L.sa_set_profiling(h, 0))
+    term_ms = stats.term_kernel_ms / prof_steps
+    launches_per_step = stats.term_kernel_launches / prof_steps
+    achieved = alg_bytes_step / (term_ms / 1e3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "term_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
+                "avg_launch_ms": term_ms / launches_per_step, "launches_per_step": launches_per_step,
+                "topk_select_ms_per_step": stats.topk_kernel_ms / prof_steps,
+                "kernel_share_of_step": term_ms / (dev_ms / args.steps)}
+
+    # ---- e2e_dense: the literal .score() drop-in, dense float32[N] to the host per query
+    e2e_dense = None
+    if rank == 0 and world == 1:
+        from searcharray_b200.postings import _pool
+        out = _pool.empty_f32(host.n_docs)
+        nd = min(Q, 96)
+        for i in range(3):
+            _lib.check(L.sa_score_term(h, int(term_ids[i]), float(idf[i]), float(avgdl), K1, B, 0, _lib.ALL_BITS,
+                                       _lib.p_f32(out)))
+        t0 = time.perf_counter()
+        for i in range(nd):
+            _lib.check(L.sa_score_term(h, int(term_ids[i]), float(idf[i]), float(avgdl), K1, B, 0, _lib.ALL_BITS,
+                                       _lib.p_f32(out)))
+        dt = time.perf_counter() - t0
+        e2e_dense = {"value": nd / dt, "unit": "queries/s", "d2h_bytes_per_query": int(host.n_docs * 4),
+                     "note": "SearchArray.score drop-in: one sa_score_term call per query, pinned result vector"}
+
+    # ---- cpu_baseline (rank 0, N=1): oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        idx, one = cpu_reference_runner(host, avgdl, args.docs, k)
+        for t in np.unique(term_ids):
+            idx.docfreq(int(t))
+            idx.termfreqs(int(t))
+        sample = term_ids[:min(Q, args.ref_sample)]
+        run_cpu_sample(one, sample[:max(8, len(sample) // 8)], cores)
+        tt, n = 0.0, 0
+        while tt < 10.0 and n < 8:
+            tt += run_cpu_sample(one, sample, cores)
+            n += 1
+        cpu = {"value": n * len(sample) / tt, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{n} x {len(sample)} of the step's queries, ThreadPool({cores}), warm tf cache, "
+                         "score over all N + argpartition top-k"}
+        # parity spot-check of the GPU top-k against the oracle on the sample
+        bad = 0
+        for qi in range(min(16, len(sample))):
+            ref = one(int(sample[qi]))
+            s_ref = idx.score(int(sample[qi]), k1=K1, b=B)
+            order = np.lexsort((np.arange(len(s_ref)), -s_ref.astype(np.float64)))[:k]
+            if not np.array_equal(out_docs[qi], order.astype(np.uint32)):
+                bad += 1
+            del ref
+        cpu["gpu_topk_mismatches_in_16"] = bad
+
+    if rank == 0:
+        line = {
+            "metric": "queries/sec (single-term BM25 + top-k) on 10M-doc synthetic MSMARCO",
+            "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, Q),
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_value,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e_dense": e2e_dense,
+            "topk_overflow_reruns": int(overflow),
+        }
+        print(json.dumps(line), flush=True)
+    dev.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--queries", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--ref-sample", type=int, default=192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        bench_reference(args, rank, world)
+    else:
+        bench_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,19 @@ int sa_score_batch_topk(sa_index *index, const uint32_t *terms, const uint32_t *
                         float avg_doc_len, float k1, float b, uint32_t k,
                         uint32_t *out_docs, float *out_scores);
 
+/* The same batch in three stages, so a serving loop (or the benchmark) can keep the query
+ * descriptors resident and time the device work alone: upload (H2D of descriptors), execute
+ * (enqueue kernels only, asynchronous), download (sync, overflow repair, D2H of the top-k;
+ * *n_overflow = queries whose candidate list overflowed and were re-run exactly). */
+int sa_batch_upload(sa_index *index, const uint32_t *terms, const uint32_t *term_starts,
+                    const float *idf, uint32_t n_queries, uint32_t slop,
+                    float avg_doc_len, float k1, float b, uint32_t k);
+int sa_batch_execute(sa_index *index);
+int sa_batch_download(sa_index *index, uint32_t *out_docs, float *out_scores, uint32_t *n_overflow);
+/* CUDA-event timer on the library's own stream (the stream the kernels are launched on). */
+int sa_timer_start(sa_index *index);
+int sa_timer_stop(sa_index *index, double *ms_out);
+
 /* Kernel-time accounting for roofline reporting (CUDA events on the library's stream):
  * milliseconds spent in, and launches of, the dominant kernels since the last reset. */
 typedef struct {
@@ -147,6 +160,10 @@ int sa_comm_destroy(sa_index *index);
  * (bench.py uses these for the barrier + max-over-ranks timing rule). */
 int sa_comm_barrier(sa_index *index);
 int sa_comm_allreduce_max(sa_index *index, double *inout);
+int sa_comm_allreduce_sum_u64(sa_index *index, uint64_t *inout, uint64_t n);
+int sa_batch_execute_allgather(sa_index *index);
+int sa_batch_download_allgather(sa_index *index, uint32_t *out_docs, float *out_scores,
+                                uint32_t *n_overflow);
 /* Like sa_score_batch_topk on every rank's shard, then ncclAllGather of the per-shard
  * (doc, score) lists and a k-way merge on the device; every rank receives the global top-k. */
 int sa_score_batch_topk_allgather(sa_index *index, const uint32_t *terms, const uint32_t *term_starts,

@@ -269,7 +269,12 @@ class OracleIndex:
     middle_out.py:291-317; postings.py:344-358)."""
 
     def __init__(self, term_words, doc_lens, avg_doc_length=None, rows=None, corpus_size=None,
-                 max_doc_id=None):
+                 max_doc_id=None, cache=False):
+        # cache=True reproduces PosnBitArray's docfreq_cache / termfreq_cache
+        # (phrase/middle_out.py:326-327,501-528): the reference's steady ("warm") state.
+        self.cache = cache
+        self._df_cache = {}
+        self._tf_cache = {}
         self.term_words = term_words          # {term_id: np.uint64[]}
         self.doc_lens = np.asarray(doc_lens, dtype=np.float32)
         self.rows = None if rows is None else np.asarray(rows, dtype=np.uint64)
@@ -310,6 +315,13 @@ class OracleIndex:
         """postings.py:640-647; on a slice df comes from the filtered postings (quirk iii)."""
         if term_id is None or term_id not in self.term_words:
             return 0
+        if self.cache and self.rows is None:
+            if term_id not in self._df_cache:
+                df = docfreq(self.term_words[term_id])
+                if len(self.term_words[term_id]) <= 25:      # cache_gt_than (middle_out.py:517-519)
+                    return df
+                self._df_cache[term_id] = df
+            return self._df_cache[term_id]
         return docfreq(self._words(term_id))
 
     def termfreqs(self, term_ids, slop=0, min_posn=None, max_posn=None):
@@ -330,6 +342,15 @@ class OracleIndex:
         w = self.term_words[term_ids]
         if min_posn is not None or max_posn is not None:
             w = slice_words(w, min_payload=min_posn, max_payload=max_posn)
+        elif self.cache:
+            # _termfreqs_with_cache (middle_out.py:501-509): cached iff the df is cached
+            if term_ids not in self._tf_cache:
+                ids, tfs = termfreqs_sparse(w)
+                if term_ids not in self._df_cache:
+                    return ops.as_dense(ids, tfs, n) if len(ids) else np.zeros(n, dtype=np.float32)
+                self._tf_cache[term_ids] = (ids, tfs)
+            ids, tfs = self._tf_cache[term_ids]
+            return ops.as_dense(ids, tfs, n) if len(ids) else np.zeros(n, dtype=np.float32)
         return termfreqs_dense(w, n)
 
     def _phrase_freq(self, term_ids, slop, min_posn, max_posn):

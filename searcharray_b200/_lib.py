@@ -46,6 +46,11 @@ SIGNATURES = {
     "sa_score_phrase": (c_int, [P_void, P_u32, c_u32, c_u32, c_f32, c_f32, c_f32, c_f32, c_u64, c_u64, P_f32]),
     "sa_score_batch_topk": (c_int, [P_void, P_u32, P_u32, P_f32, c_u32, c_u32, c_f32, c_f32, c_f32, c_u32,
                                     P_u32, P_f32]),
+    "sa_batch_upload": (c_int, [P_void, P_u32, P_u32, P_f32, c_u32, c_u32, c_f32, c_f32, c_f32, c_u32]),
+    "sa_batch_execute": (c_int, [P_void]),
+    "sa_batch_download": (c_int, [P_void, P_u32, P_f32, P_u32]),
+    "sa_timer_start": (c_int, [P_void]),
+    "sa_timer_stop": (c_int, [P_void, ctypes.POINTER(ctypes.c_double)]),
     "sa_stats_reset": (c_int, [P_void]),
     "sa_stats_get": (c_int, [P_void, ctypes.POINTER(SaStats)]),
     "sa_set_profiling": (c_int, [P_void, c_int]),
@@ -54,6 +59,9 @@ SIGNATURES = {
     "sa_comm_destroy": (c_int, [P_void]),
     "sa_comm_barrier": (c_int, [P_void]),
     "sa_comm_allreduce_max": (c_int, [P_void, ctypes.POINTER(ctypes.c_double)]),
+    "sa_comm_allreduce_sum_u64": (c_int, [P_void, P_u64, c_u64]),
+    "sa_batch_execute_allgather": (c_int, [P_void]),
+    "sa_batch_download_allgather": (c_int, [P_void, P_u32, P_f32, P_u32]),
     "sa_score_batch_topk_allgather": (c_int, [P_void, P_u32, P_u32, P_f32, c_u32, c_u32, c_f32, c_f32, c_f32,
                                               c_u32, P_u32, P_f32]),
     "sa_op_popcount64_reduce": (c_int, [P_u64, c_u64, c_int, P_u64, P_f32, P_u64]),

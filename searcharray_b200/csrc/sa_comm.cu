@@ -71,26 +71,77 @@ extern "C" int sa_comm_allreduce_max(sa_index *ix, double *inout) {
     return SA_OK;
 }
 
+// enqueue: all-gather the per-shard result keys and merge (async on the library stream)
+static int enqueue_allgather_merge(sa_index *ix, size_t nq, u32 k) {
+    const size_t nk = nq * k;
+    if (nk == 0) return SA_OK;
+    int rc;
+    if ((rc = ix->gather.reserve(((size_t)ix->world + 1) * nk * sizeof(u64)))) return rc;
+    u64 *d_all = ix->gather.as<u64>();
+    u64 *d_merged = d_all + (size_t)ix->world * nk;
+    SA_NCCL(ncclAllGather(ix->topk_out.p, d_all, nk, ncclUint64, (ncclComm_t)ix->nccl_comm, ix->stream));
+    return launch_topk_merge(ix, d_all, (u32)ix->world, (u32)nq, k, d_merged);
+}
+
+extern "C" int sa_batch_execute_allgather(sa_index *ix) {
+    SA_CHECK(ix && ix->nccl_comm, "communicator not initialised (sa_comm_init)");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = sa_batch_execute_locked(ix);
+    if (rc) return rc;
+    u32 nq, k;
+    sa_batch_dims(ix, &nq, &k);
+    return enqueue_allgather_merge(ix, nq, k);
+}
+
+extern "C" int sa_batch_download_allgather(sa_index *ix, uint32_t *out_docs, float *out_scores,
+                                           uint32_t *n_overflow) {
+    SA_CHECK(ix && ix->nccl_comm && out_docs && out_scores, "NULL argument / no communicator");
+    std::lock_guard<std::mutex> g(ix->mu);
+    u32 nq, k, redone = 0;
+    sa_batch_dims(ix, &nq, &k);
+    int rc = sa_batch_fix_overflow_locked(ix, &redone);
+    if (rc) return rc;
+    if (n_overflow) *n_overflow = redone;
+    // every rank must take the same path: agree on "somebody re-ran a query"
+    int rc2 = ix->misc.reserve(256);
+    if (rc2) return rc2;
+    float flag = redone ? 1.0f : 0.0f;
+    SA_CUDA(cudaMemcpyAsync(ix->misc.p, &flag, sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    SA_NCCL(ncclAllReduce(ix->misc.p, ix->misc.p, 1, ncclFloat, ncclMax, (ncclComm_t)ix->nccl_comm, ix->stream));
+    SA_CUDA(cudaMemcpyAsync(&flag, ix->misc.p, sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    if (flag != 0.0f && (rc = enqueue_allgather_merge(ix, nq, k))) return rc;
+    const size_t nk = (size_t)nq * k;
+    if (nk == 0) return SA_OK;
+    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
+    const u64 *d_merged = ix->gather.as<u64>() + (size_t)ix->world * nk;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_merged, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    return SA_OK;
+}
+
 extern "C" int sa_score_batch_topk_allgather(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
                                              const float *idf, uint32_t n_queries, uint32_t slop,
                                              float avg_doc_len, float k1, float b, uint32_t k,
                                              uint32_t *out_docs, float *out_scores) {
     SA_CHECK(ix && out_docs && out_scores, "NULL argument");
-    SA_CHECK(ix->nccl_comm, "communicator not initialised (sa_comm_init)");
-    std::lock_guard<std::mutex> g(ix->mu);
-    int rc = sa_batch_topk_device(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
+    int rc = sa_batch_upload(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
     if (rc) return rc;
-    const size_t nk = (size_t)n_queries * k;
-    if (nk == 0) return SA_OK;
-    // [world][Q][k] gathered keys, then [Q][k] merged
-    if ((rc = ix->gather.reserve(((size_t)ix->world + 1) * nk * sizeof(u64)))) return rc;
-    u64 *d_all = ix->gather.as<u64>();
-    u64 *d_merged = d_all + (size_t)ix->world * nk;
-    SA_NCCL(ncclAllGather(ix->topk_out.p, d_all, nk, ncclUint64, (ncclComm_t)ix->nccl_comm, ix->stream));
-    if ((rc = launch_topk_merge(ix, d_all, (u32)ix->world, n_queries, k, d_merged))) return rc;
-    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_merged, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    if ((rc = sa_batch_execute_allgather(ix))) return rc;
+    return sa_batch_download_allgather(ix, out_docs, out_scores, nullptr);
+}
+
+extern "C" int sa_comm_allreduce_sum_u64(sa_index *ix, uint64_t *inout, uint64_t n) {
+    SA_CHECK(ix && ix->nccl_comm && (inout || n == 0), "communicator not initialised");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    if (n == 0) return SA_OK;
+    int rc = ix->misc.reserve(n * sizeof(u64));
+    if (rc) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->misc.p, inout, n * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+    SA_NCCL(ncclAllReduce(ix->misc.p, ix->misc.p, n, ncclUint64, ncclSum, (ncclComm_t)ix->nccl_comm, ix->stream));
+    SA_CUDA(cudaMemcpyAsync(inout, ix->misc.p, n * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
-    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
     return SA_OK;
 }

@@ -90,6 +90,8 @@ struct TermQuery {
 };
 
 // ---- the index handle ---------------------------------------------------------------
+struct TimedLaunch;
+struct BatchState;
 struct sa_index {
     int device = 0;
     int num_sms = SA_NUM_SMS_FALLBACK;
@@ -111,8 +113,11 @@ struct sa_index {
     unsigned char *d_row_mask = nullptr;  // [n_docs] 1 if doc selected
 
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // sa_timer_start / sa_timer_stop
     bool profiling = false;
+    std::vector<struct TimedLaunch> *pending_timers = nullptr;
+    std::vector<cudaEvent_t> *free_events = nullptr;
+    struct BatchState *batch = nullptr;
     sa_stats stats;
     std::mutex mu;
 
@@ -137,24 +142,18 @@ struct sa_index {
 
 int sa_pinned_reserve(sa_index *ix, size_t bytes);
 
-// kernel timing helper: records events around a launch sequence when profiling is on
+// Kernel timing without serialising the stream: when profiling is on every timed launch gets
+// an event pair from a pool; elapsed times are resolved lazily (sa_stats_get syncs once).
+struct TimedLaunch { cudaEvent_t e0, e1; int kind; };   // kind: 0 term, 1 topk, 2 phrase
 struct KernelTimer {
     sa_index *ix;
-    double *acc_ms;
+    int kind;
     bool on;
-    KernelTimer(sa_index *ix_, double *acc) : ix(ix_), acc_ms(acc), on(ix_->profiling) {
-        if (on) cudaEventRecord(ix->ev0, ix->stream);
-    }
-    void stop() {
-        if (!on) return;
-        cudaEventRecord(ix->ev1, ix->stream);
-        cudaEventSynchronize(ix->ev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ix->ev0, ix->ev1);
-        *acc_ms += ms;
-        on = false;
-    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(sa_index *ix_, int kind_);
+    void stop();
 };
+int sa_resolve_timers(sa_index *ix);
 
 // ---- device helpers -------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -166,6 +166,8 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
     return SA_OK;
 }
 
+void sa_free_batch(sa_index *ix);
+
 extern "C" int sa_index_destroy(sa_index *ix) {
     if (!ix) return SA_OK;
     cudaSetDevice(ix->device);
@@ -184,6 +186,15 @@ extern "C" int sa_index_destroy(sa_index *ix) {
     ix->phrase_scratch.release();
     ix->misc.release();
     ix->gather.release();
+    sa_free_batch(ix);
+    if (ix->pending_timers) {
+        for (auto &t : *ix->pending_timers) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+        delete ix->pending_timers;
+    }
+    if (ix->free_events) {
+        for (auto e : *ix->free_events) cudaEventDestroy(e);
+        delete ix->free_events;
+    }
     if (ix->h_pinned) cudaFreeHost(ix->h_pinned);
     if (ix->ev0) cudaEventDestroy(ix->ev0);
     if (ix->ev1) cudaEventDestroy(ix->ev1);
@@ -213,6 +224,7 @@ extern "C" int sa_docfreq(sa_index *ix, uint32_t term_id, uint64_t *df_out) {
 extern "C" int sa_stats_reset(sa_index *ix) {
     SA_CHECK(ix, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    sa_resolve_timers(ix);
     memset(&ix->stats, 0, sizeof(ix->stats));
     return SA_OK;
 }
@@ -220,6 +232,8 @@ extern "C" int sa_stats_reset(sa_index *ix) {
 extern "C" int sa_stats_get(sa_index *ix, sa_stats *out) {
     SA_CHECK(ix && out, "NULL argument");
     std::lock_guard<std::mutex> g(ix->mu);
+    int rc = sa_resolve_timers(ix);
+    if (rc) return rc;
     *out = ix->stats;
     return SA_OK;
 }
@@ -307,45 +321,16 @@ extern "C" int sa_score_term(sa_index *ix, uint32_t term_id, float idf, float av
 }
 
 // ------------------------------------------------ batched, HBM-resident top-k
-// One chunk: score Q queries into ix->dense, collect candidates, select top-k into d_keys.
-static int run_topk_chunk(sa_index *ix, const std::vector<TermQuery> &qs, const Bm25Params &p,
-                          u32 k, u32 cap, u64 *d_keys) {
-    const u32 Q = (u32)qs.size();
-    const u64 stride = padded_docs(ix->n_docs);
-    int rc;
-    if ((rc = ix->dense.reserve((size_t)Q * stride * sizeof(float)))) return rc;
-    if ((rc = ix->queries.reserve((size_t)Q * sizeof(TermQuery)))) return rc;
-    if ((rc = ix->cand.reserve((size_t)Q * cap * sizeof(u64)))) return rc;
-    if ((rc = ix->cand_meta.reserve((size_t)Q * 2 * sizeof(u32)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->queries.p, qs.data(), (size_t)Q * sizeof(TermQuery), cudaMemcpyHostToDevice, ix->stream));
-    SA_CUDA(cudaMemsetAsync(ix->cand_meta.p, 0, (size_t)Q * 2 * sizeof(u32), ix->stream));
-    TermBatchArgs a;
-    memset(&a, 0, sizeof(a));
-    a.words = ix->d_words;
-    a.doc_lens = ix->d_doc_lens;
-    a.n_docs = ix->n_docs;
-    a.doc_base = ix->doc_base;
-    a.queries = ix->queries.as<TermQuery>();
-    a.out = ix->dense.as<float>();
-    a.out_stride = stride;
-    a.bm25 = p;
-    a.min_payload = 0;
-    a.max_payload = SA_ALL_BITS;
-    a.filter = 0;
-    a.mode = TERM_MODE_SCORE;
-    a.topk.thr_bits = ix->cand_meta.as<u32>();
-    a.topk.count = ix->cand_meta.as<u32>() + Q;
-    a.topk.cand = ix->cand.as<u64>();
-    a.topk.cap = cap;
-    a.topk.k = k;
-    if ((rc = launch_term_batch(ix, a, Q))) return rc;
-    if ((rc = launch_topk_select(ix, a.topk, Q, ix->doc_base, d_keys))) return rc;
-    // candidate counts back to the host (overflow check)
-    if ((rc = sa_pinned_reserve(ix, std::max<size_t>((size_t)Q * sizeof(u32), 4096)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, a.topk.count, (size_t)Q * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
-    SA_CUDA(cudaStreamSynchronize(ix->stream));
-    return SA_OK;
-}
+// A prepared batch: query descriptors live in HBM; sa_batch_execute only enqueues kernels.
+struct BatchState {
+    u32 nq = 0, k = 0, cap = 0, chunk = 0;
+    float avg_doc_len = 0, k1 = 0, b = 0;
+    bool ready = false;
+    std::vector<TermQuery> qs;
+    std::vector<Bm25Params> chunk_params;     // per chunk (sparse_ok must hold for every idf in it)
+    DevBuf d_queries;                          // TermQuery[nq]
+    DevBuf d_meta;                             // u32 thr[nq], u32 count[nq]
+};
 
 static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     TermQuery tq;
@@ -355,50 +340,130 @@ static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     return tq;
 }
 
-int sa_batch_topk_device(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
-                         const float *idf, uint32_t n_queries, uint32_t slop,
-                         float avg_doc_len, float k1, float b, uint32_t k) {
+// Enqueue scoring + candidate collection + select for queries [q0, q0+Q) (async).
+static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_thr, u32 *d_count,
+                              u32 Q, const Bm25Params &p, u32 k, u32 cap, u64 *d_keys) {
+    const u64 stride = padded_docs(ix->n_docs);
+    TermBatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.words = ix->d_words;
+    a.doc_lens = ix->d_doc_lens;
+    a.n_docs = ix->n_docs;
+    a.doc_base = ix->doc_base;
+    a.queries = d_queries;
+    a.out = ix->dense.as<float>();
+    a.out_stride = stride;
+    a.bm25 = p;
+    a.min_payload = 0;
+    a.max_payload = SA_ALL_BITS;
+    a.filter = 0;
+    a.mode = TERM_MODE_SCORE;
+    a.topk.thr_bits = d_thr;
+    a.topk.count = d_count;
+    a.topk.cand = ix->cand.as<u64>();
+    a.topk.cap = cap;
+    a.topk.k = k;
+    int rc;
+    if ((rc = launch_term_batch(ix, a, Q))) return rc;
+    return launch_topk_select(ix, a.topk, Q, ix->doc_base, d_keys);
+}
+
+int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                           const float *idf, uint32_t n_queries, uint32_t slop,
+                           float avg_doc_len, float k1, float b, uint32_t k) {
     (void)slop;
-    SA_CHECK(ix && terms && term_starts && idf, "NULL argument");
+    SA_CHECK(ix && (n_queries == 0 || (terms && term_starts && idf)), "NULL argument");
     SA_CHECK(k >= 1 && k <= SA_TOPK_MAX, "k must be in [1, %d]", SA_TOPK_MAX);
     SA_CUDA(cudaSetDevice(ix->device));
+    if (!ix->batch) ix->batch = new BatchState();
+    BatchState &B = *ix->batch;
+    B.ready = false;
+    B.nq = n_queries;
+    B.k = k;
+    B.avg_doc_len = avg_doc_len;
+    B.k1 = k1;
+    B.b = b;
+    B.qs.clear();
+    B.chunk_params.clear();
     int rc;
     if ((rc = ix->topk_out.reserve(std::max<size_t>((size_t)n_queries * k * sizeof(u64), 256)))) return rc;
-    u64 *d_keys = ix->topk_out.as<u64>();
-    SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)n_queries * k * sizeof(u64), ix->stream));
-    if (ix->n_docs == 0 || n_queries == 0 || avg_doc_len == 0.0f) return SA_OK;
-    const u64 stride = padded_docs(ix->n_docs);
+    if (n_queries == 0) { B.ready = true; return SA_OK; }
+    const u64 stride = padded_docs(std::max<u64>(ix->n_docs, 1));
     // chunk so the dense score vectors of one chunk stay within ~4 GB of HBM
     u32 chunk = (u32)std::max<u64>(1, std::min<u64>(n_queries, (4ull << 30) / (stride * sizeof(float))));
-    chunk = std::min<u32>(chunk, 65535);
-    const u32 cap = (u32)std::min<u64>(ix->n_docs, 1u << 16);
-    std::vector<TermQuery> qs;
-    std::vector<u32> redo;
-    for (u32 q0 = 0; q0 < n_queries; q0 += chunk) {
-        const u32 Q = std::min(chunk, n_queries - q0);
-        qs.clear();
+    B.chunk = std::min<u32>(chunk, 65535);
+    B.cap = (u32)std::max<u64>(1, std::min<u64>(ix->n_docs, 1u << 16));
+    for (u32 q = 0; q < n_queries; q++) {
+        SA_CHECK(term_starts[q + 1] - term_starts[q] == 1,
+                 "query %u: phrase queries in a batch are not supported yet", q);
+        u32 t = terms[term_starts[q]];
+        SA_CHECK(t == SA_NO_TERM || t < ix->n_terms, "term id %u out of range", t);
+        B.qs.push_back(make_term_query(ix, t, idf[q]));
+    }
+    for (u32 q0 = 0; q0 < n_queries; q0 += B.chunk) {
         Bm25Params p = make_bm25(ix, 1.0f, avg_doc_len, k1, b);
-        for (u32 q = q0; q < q0 + Q; q++) {
-            SA_CHECK(term_starts[q + 1] - term_starts[q] == 1,
-                     "query %u: phrase queries in a batch are not supported yet", q);
-            u32 t = terms[term_starts[q]];
-            SA_CHECK(t == SA_NO_TERM || t < ix->n_terms, "term id %u out of range", t);
-            qs.push_back(make_term_query(ix, t, idf[q]));
-            // sparse_ok must hold for every idf in the chunk
+        for (u32 q = q0; q < std::min(n_queries, q0 + B.chunk); q++)
             if (!make_bm25(ix, idf[q], avg_doc_len, k1, b).sparse_ok) p.sparse_ok = 0;
-        }
-        if ((rc = run_topk_chunk(ix, qs, p, k, cap, d_keys + (u64)q0 * k))) return rc;
-        const u32 *counts = (const u32 *)ix->h_pinned;
-        for (u32 q = 0; q < Q; q++) if (counts[q] > cap) redo.push_back(q0 + q);
+        B.chunk_params.push_back(p);
     }
-    // candidate overflow (threshold rose too slowly, e.g. scores ascending with doc id or
-    // massive ties): re-run those queries one at a time with room for every doc.
+    if ((rc = ix->dense.reserve((size_t)B.chunk * stride * sizeof(float)))) return rc;
+    if ((rc = ix->cand.reserve((size_t)B.chunk * B.cap * sizeof(u64)))) return rc;
+    if ((rc = B.d_queries.reserve((size_t)n_queries * sizeof(TermQuery)))) return rc;
+    if ((rc = B.d_meta.reserve((size_t)n_queries * 2 * sizeof(u32)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(B.d_queries.p, B.qs.data(), (size_t)n_queries * sizeof(TermQuery),
+                            cudaMemcpyHostToDevice, ix->stream));
+    B.ready = true;
+    return SA_OK;
+}
+
+int sa_batch_execute_locked(sa_index *ix) {
+    SA_CHECK(ix && ix->batch && ix->batch->ready, "no batch uploaded (sa_batch_upload)");
+    BatchState &B = *ix->batch;
+    SA_CUDA(cudaSetDevice(ix->device));
+    u64 *d_keys = ix->topk_out.as<u64>();
+    if (B.nq == 0) return SA_OK;
+    SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)B.nq * B.k * sizeof(u64), ix->stream));
+    if (ix->n_docs == 0 || B.avg_doc_len == 0.0f) return SA_OK;
+    u32 *d_thr = B.d_meta.as<u32>(), *d_count = d_thr + B.nq;
+    SA_CUDA(cudaMemsetAsync(d_thr, 0, (size_t)B.nq * 2 * sizeof(u32), ix->stream));
+    u32 ci = 0;
+    for (u32 q0 = 0; q0 < B.nq; q0 += B.chunk, ci++) {
+        const u32 Q = std::min(B.chunk, B.nq - q0);
+        int rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q0, d_thr + q0, d_count + q0, Q,
+                                    B.chunk_params[ci], B.k, B.cap, d_keys + (u64)q0 * B.k);
+        if (rc) return rc;
+    }
+    return SA_OK;
+}
+
+// After execute: re-run (synchronously) the queries whose candidate list overflowed.
+int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
+    BatchState &B = *ix->batch;
+    if (n_redone) *n_redone = 0;
+    if (B.nq == 0 || ix->n_docs == 0 || B.avg_doc_len == 0.0f) return SA_OK;
+    int rc;
+    if ((rc = sa_pinned_reserve(ix, std::max<size_t>((size_t)B.nq * sizeof(u32), 4096)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, B.d_meta.as<u32>() + B.nq, (size_t)B.nq * sizeof(u32),
+                            cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    std::vector<u32> redo;
+    const u32 *counts = (const u32 *)ix->h_pinned;
+    for (u32 q = 0; q < B.nq; q++) if (counts[q] > B.cap) redo.push_back(q);
+    if (redo.empty()) return SA_OK;
+    // candidate overflow (threshold rose too slowly, e.g. scores ascending with doc id, or
+    // massive ties): one query at a time with room for every doc.
+    if ((rc = ix->cand.reserve((size_t)ix->n_docs * sizeof(u64)))) return rc;
+    u32 *d_thr = B.d_meta.as<u32>(), *d_count = d_thr + B.nq;
     for (u32 q : redo) {
-        qs.clear();
-        qs.push_back(make_term_query(ix, terms[term_starts[q]], idf[q]));
-        Bm25Params p = make_bm25(ix, idf[q], avg_doc_len, k1, b);
-        if ((rc = run_topk_chunk(ix, qs, p, k, (u32)ix->n_docs, d_keys + (u64)q * k))) return rc;
+        SA_CUDA(cudaMemsetAsync(d_thr + q, 0, sizeof(u32), ix->stream));
+        SA_CUDA(cudaMemsetAsync(d_count + q, 0, sizeof(u32), ix->stream));
+        Bm25Params p = make_bm25(ix, B.qs[q].idf, B.avg_doc_len, B.k1, B.b);
+        rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q, d_thr + q, d_count + q, 1, p, B.k,
+                                (u32)ix->n_docs, ix->topk_out.as<u64>() + (u64)q * B.k);
+        if (rc) return rc;
     }
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    if (n_redone) *n_redone = (u32)redo.size();
     return SA_OK;
 }
 
@@ -412,19 +477,121 @@ void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_score
     }
 }
 
+static int download_keys(sa_index *ix, const u64 *d_keys, size_t nk, uint32_t *out_docs, float *out_scores) {
+    if (nk == 0) return SA_OK;
+    int rc;
+    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_keys, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    return SA_OK;
+}
+
+extern "C" int sa_batch_upload(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                               const float *idf, uint32_t n_queries, uint32_t slop,
+                               float avg_doc_len, float k1, float b, uint32_t k) {
+    SA_CHECK(ix, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return sa_batch_upload_locked(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
+}
+
+extern "C" int sa_batch_execute(sa_index *ix) {
+    SA_CHECK(ix, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    return sa_batch_execute_locked(ix);
+}
+
+extern "C" int sa_batch_download(sa_index *ix, uint32_t *out_docs, float *out_scores, uint32_t *n_overflow) {
+    SA_CHECK(ix && ix->batch && ix->batch->ready, "no batch uploaded");
+    SA_CHECK(out_docs && out_scores, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = sa_batch_fix_overflow_locked(ix, n_overflow);
+    if (rc) return rc;
+    return download_keys(ix, ix->topk_out.as<u64>(), (size_t)ix->batch->nq * ix->batch->k, out_docs, out_scores);
+}
+
 extern "C" int sa_score_batch_topk(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
                                    const float *idf, uint32_t n_queries, uint32_t slop,
                                    float avg_doc_len, float k1, float b, uint32_t k,
                                    uint32_t *out_docs, float *out_scores) {
     SA_CHECK(ix && out_docs && out_scores, "NULL argument");
     std::lock_guard<std::mutex> g(ix->mu);
-    int rc = sa_batch_topk_device(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
+    int rc = sa_batch_upload_locked(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
     if (rc) return rc;
-    const size_t nk = (size_t)n_queries * k;
-    if (nk == 0) return SA_OK;
-    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, ix->topk_out.p, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    if ((rc = sa_batch_execute_locked(ix))) return rc;
+    if ((rc = sa_batch_fix_overflow_locked(ix, nullptr))) return rc;
+    return download_keys(ix, ix->topk_out.as<u64>(), (size_t)n_queries * k, out_docs, out_scores);
+}
+
+// ------------------------------------------------------------------- timers
+KernelTimer::KernelTimer(sa_index *ix_, int kind_) : ix(ix_), kind(kind_), on(ix_->profiling) {
+    if (!on) return;
+    if (!ix->pending_timers) ix->pending_timers = new std::vector<TimedLaunch>();
+    if (!ix->free_events) ix->free_events = new std::vector<cudaEvent_t>();
+    auto get = [&]() {
+        cudaEvent_t e = nullptr;
+        if (!ix->free_events->empty()) { e = ix->free_events->back(); ix->free_events->pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    e0 = get();
+    e1 = get();
+    cudaEventRecord(e0, ix->stream);
+}
+
+void KernelTimer::stop() {
+    if (!on) return;
+    cudaEventRecord(e1, ix->stream);
+    ix->pending_timers->push_back(TimedLaunch{e0, e1, kind});
+    on = false;
+}
+
+int sa_resolve_timers(sa_index *ix) {
+    if (!ix->pending_timers || ix->pending_timers->empty()) return SA_OK;
     SA_CUDA(cudaStreamSynchronize(ix->stream));
-    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    for (auto &t : *ix->pending_timers) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        if (t.kind == 0) ix->stats.term_kernel_ms += ms;
+        else if (t.kind == 1) ix->stats.topk_kernel_ms += ms;
+        else ix->stats.phrase_kernel_ms += ms;
+        ix->free_events->push_back(t.e0);
+        ix->free_events->push_back(t.e1);
+    }
+    ix->pending_timers->clear();
     return SA_OK;
+}
+
+extern "C" int sa_timer_start(sa_index *ix) {
+    SA_CHECK(ix, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    SA_CUDA(cudaEventRecord(ix->ev0, ix->stream));
+    return SA_OK;
+}
+
+extern "C" int sa_timer_stop(sa_index *ix, double *ms_out) {
+    SA_CHECK(ix && ms_out, "NULL argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    SA_CUDA(cudaEventRecord(ix->ev1, ix->stream));
+    SA_CUDA(cudaEventSynchronize(ix->ev1));
+    float ms = 0;
+    SA_CUDA(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+    *ms_out = ms;
+    return SA_OK;
+}
+
+void sa_free_batch(sa_index *ix) {
+    if (!ix->batch) return;
+    ix->batch->d_queries.release();
+    ix->batch->d_meta.release();
+    delete ix->batch;
+    ix->batch = nullptr;
+}
+
+void sa_batch_dims(sa_index *ix, u32 *nq, u32 *k) {
+    *nq = ix->batch ? ix->batch->nq : 0;
+    *k = ix->batch ? ix->batch->k : 0;
 }

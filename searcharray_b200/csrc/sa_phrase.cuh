@@ -1,0 +1,55 @@
+// sa_phrase.cuh -- declarations for the phrase (slop == 0) path.
+#pragma once
+#include "sa_common.cuh"
+
+#define SA_PHRASE_THREADS 256
+#define SA_PHRASE_MODE_LR 0      // left-to-right chain  (reference middle_out.py:96-122)
+#define SA_PHRASE_MODE_RL 1      // right-to-left chain  (reference middle_out.py:125-151)
+#define SA_PHRASE_MODE_MID 2     // middle-out: LR on [0,split), RL on [split,n), then and/min (:163-168)
+
+// One phrase query against one shard.
+struct PhraseQuery {
+    u32 n_terms;
+    u32 mode;
+    u32 split;            // SA_PHRASE_MODE_MID only
+    u32 same_guess;       // bit s set => step s is speculated to take the "same term" branch
+    u64 off[SA_MAX_PHRASE_TERMS];   // word offset of each term's list (relative to `words`)
+    u64 len[SA_MAX_PHRASE_TERMS];
+    float idf;
+    u32 pad;
+};
+
+struct PhraseStats {      // per query, accumulated over all chunks (global atomics)
+    u32 n_inner[SA_MAX_PHRASE_TERMS];   // equal-header pairs seen at step s
+    u32 n_diff[SA_MAX_PHRASE_TERMS];    // ... of which lhs word != rhs word
+    u32 overflow;                        // scratch arena exhausted
+    u32 pad;
+};
+
+// Optional dump of one CTA's final lists (per-op parity export; needs n_chunks == 1).
+struct PhraseDump {
+    u64 *cont;        // continuation words of the last step
+    u64 *n_cont;
+    u64 *docs;        // doc << 32 | count of the last step (BEFORE and/min with earlier steps)
+    u64 *n_docs;
+};
+
+struct PhraseArgs {
+    const u64 *words;           // lists live at words + off
+    const float *doc_lens;
+    u64 n_docs, doc_base;
+    const PhraseQuery *queries;
+    PhraseStats *stats;
+    float *out;                 // [Q][out_stride], pre-zeroed
+    u64 out_stride;
+    u32 n_chunks;               // doc-range chunks per query (grid.x)
+    u64 docs_per_chunk;
+    u64 *arena;                 // scratch bump arena (u64 words)
+    unsigned long long *arena_used;
+    u64 arena_cap;
+    Bm25Params bm25;
+    int score;                  // 0: write phrase freqs, 1: BM25 (sparse)
+    PhraseDump dump;
+};
+
+int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries);

@@ -191,7 +191,7 @@ int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries) {
     if (n_queries == 0 || a.n_docs == 0) return SA_OK;
     dim3 grid((unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS), n_queries);
     dim3 block(SA_TERM_THREADS);
-    KernelTimer t(ix, &ix->stats.term_kernel_ms);
+    KernelTimer t(ix, 0);
     if (a.mode == TERM_MODE_TF)
         term_tile_kernel<TERM_MODE_TF, false><<<grid, block, 0, ix->stream>>>(a);
     else if (a.bm25.sparse_ok)

@@ -35,8 +35,11 @@ struct TermBatchArgs {
 int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries);
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys);
 int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
-// Runs the batch on this shard; leaves [n_queries][k] result keys in ix->topk_out (device).
-int sa_batch_topk_device(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
-                         const float *idf, uint32_t n_queries, uint32_t slop,
-                         float avg_doc_len, float k1, float b, uint32_t k);
+// batch plumbing shared by sa_index.cu / sa_comm.cu (callers hold ix->mu)
+int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
+                           const float *idf, uint32_t n_queries, uint32_t slop,
+                           float avg_doc_len, float k1, float b, uint32_t k);
+int sa_batch_execute_locked(sa_index *ix);
+int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone);
+void sa_batch_dims(sa_index *ix, u32 *nq, u32 *k);
 void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_scores);

@@ -126,7 +126,7 @@ topk_merge_kernel(const u64 *__restrict__ in, u32 world, u32 n_queries, u32 k, u
 
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys) {
     if (n_queries == 0) return SA_OK;
-    KernelTimer tm(ix, &ix->stats.topk_kernel_ms);
+    KernelTimer tm(ix, 1);
     topk_select_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(t, doc_base, d_out_keys);
     SA_CUDA(cudaGetLastError());
     tm.stop();
@@ -138,7 +138,7 @@ int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_ba
 int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out) {
     if (n_queries == 0) return SA_OK;
     SA_CHECK((u64)world * k <= SEL_SMEM_KEYS, "world*k too large for the merge kernel");
-    KernelTimer tm(ix, &ix->stats.topk_kernel_ms);
+    KernelTimer tm(ix, 1);
     topk_merge_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(d_in, world, n_queries, k, d_out);
     SA_CUDA(cudaGetLastError());
     tm.stop();
