@@ -1,18 +1,771 @@
-// sa_phrase.cu -- phrase / slop path (under construction) and per-op test exports.
+// sa_phrase.cu -- exact phrase matching (slop == 0) on roaringish posting words.
+//
+// Replaces (reference paths relative to softwaredoug/searcharray):
+//   compute_phrase_freqs + L->R / R->L drivers + _intersect_bigram_matches  phrase/middle_out.py:73-168
+//   bigram_freqs, _inner_bigram_freqs, _inner_bigram_same_term, _adj_to_phrase_freq,
+//   _adjacent_bigram_freqs, _set_adjbit_at_header                          phrase/bigram_freqs.py:48-307
+//   intersect_with_adjacents / intersect / merge / sort_merge_counts /
+//   popcount_reduce_at / key_sum_over                                       roaringish/*.pyx
+//   PosnBitArray.phrase_freqs dense scatter                                 phrase/middle_out.py:418-446
+//
+// Design.  Phrase matching never crosses a document, and every term's words are sorted by doc
+// id, so the doc-id space is cut into chunks and ONE CTA RUNS THE WHOLE n-TERM PIPELINE FOR ONE
+// (query, doc-range chunk): it locates each term's slice for its doc range (warp-cooperative
+// 32-ary search), then for every bigram step walks the shorter "driver" list one element per
+// thread, binary-searches the other list for the equal header and the adjacent header (the
+// reference's galloping intersect has plain set semantics on header-unique lists, SURVEY 8a row
+// 10), does the 18-bit shift/AND/popcount, emits the continuation words in order through a block
+// scan, and reduces the per-doc counts with a segmented sum.  The running min over steps is a
+// search into the previous step's (doc, count) list.  Matches are scattered into the pre-zeroed
+// dense vector, optionally through BM25.
+//
+// The reference's "same term" branch (bigram_freqs.py:139) depends on a GLOBAL property
+// (all equal-header pairs identical).  Each launch runs with a speculated flag per step and
+// counts (pairs, differing pairs) per step; the host verifies and re-launches on a mis-guess
+// (only adversarial inputs ever do).
+#include <algorithm>
+
+#include "sa_phrase.cuh"
 #include "sa_term.cuh"
 
-#define SA_TODO(name)                                \
-    do {                                             \
-        sa_set_error(name ": not implemented yet");  \
-        return SA_ERR_ARG;                           \
-    } while (0)
+#define PT SA_PHRASE_THREADS
 
-extern "C" int sa_index_set_rows(sa_index *, const uint64_t *, uint64_t) { SA_TODO("sa_index_set_rows"); }
-extern "C" int sa_docfreq_rows(sa_index *, uint32_t, uint64_t *) { SA_TODO("sa_docfreq_rows"); }
-extern "C" int sa_phrase_freqs(sa_index *, const uint32_t *, uint32_t, uint32_t, uint64_t, uint64_t, float *) { SA_TODO("sa_phrase_freqs"); }
-extern "C" int sa_score_phrase(sa_index *, const uint32_t *, uint32_t, uint32_t, float, float, float, float,
-                               uint64_t, uint64_t, float *) { SA_TODO("sa_score_phrase"); }
-extern "C" int sa_op_popcount64_reduce(const uint64_t *, uint64_t, int, uint64_t *, float *, uint64_t *) { SA_TODO("sa_op_popcount64_reduce"); }
-extern "C" int sa_op_bm25_score(float *, const float *, uint64_t, float, float, float, float, int) { SA_TODO("sa_op_bm25_score"); }
-extern "C" int sa_op_bigram_freqs(const uint64_t *, uint64_t, const uint64_t *, uint64_t, int, int,
-                                  uint64_t *, float *, uint64_t *, uint64_t *, uint64_t *) { SA_TODO("sa_op_bigram_freqs"); }
+struct Elem {
+    u64 w0, w1;
+    u32 n_emit, cnt, doc;
+    bool entry, inner, diff;
+};
+
+__device__ __forceinline__ u64 lower_bound_hdr(const u64 *__restrict__ a, u64 n, u64 target) {
+    u64 lo = 0, hi = n;
+    while (lo < hi) {
+        u64 mid = (lo + hi) >> 1;
+        if ((a[mid] & SA_HDR_MASK) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One equal-header pair (bigram_freqs.py:104-155 normal branch, :65-101 same-term branch).
+__device__ __forceinline__ void inner_calc(u64 l, u64 r, bool same, bool cont_rhs, u32 &cnt, u64 &word) {
+    if (!same) {
+        u64 ov = (l & SA_LSB_MASK) & ((r & SA_LSB_MASK) >> 1);
+        cnt = (u32)__popcll(ov);
+        word = cont_rhs ? (((ov << 1) & SA_LSB_MASK) | (r & SA_HDR_MASK)) : (ov | (l & SA_HDR_MASK));
+    } else {
+        u64 full = l & (r << 1);
+        u32 adj = (u32)__popcll(full & SA_LSB_MASK);
+        u32 runs = (u32)__popcll((full & (full << 1)) & SA_LSB_MASK);
+        cnt = adj - ((runs + 1) >> 1);                        // _adj_to_phrase_freq: - ceil(runs/2)
+        word = cont_rhs ? ((((r << 1) & r) & SA_LSB_MASK) | (l & ~SA_LSB_MASK))
+                        : ((l & ~SA_LSB_MASK) | ((l & (l >> 1)) & SA_LSB_MASK));   // `>> 1` leak kept
+    }
+}
+
+// What driver element i contributes.  D = driver list, O = the other list.
+template <bool CONT_RHS, bool DRIVER_LHS>
+__device__ __forceinline__ Elem compute_elem(const u64 *__restrict__ D, u64 nD, u64 i,
+                                             const u64 *__restrict__ O, u64 nO, bool same) {
+    Elem e;
+    e.w0 = e.w1 = 0;
+    e.n_emit = 0;
+    e.cnt = 0;
+    e.entry = e.inner = e.diff = false;
+    const u64 x = D[i];
+    const u64 h = x & SA_HDR_MASK;
+    e.doc = (u32)(x >> SA_KEY_SHIFT);
+    if (DRIVER_LHS) {
+        // x is an lhs word: partners are rhs words at header h (inner) and h + 1 block (adjacent)
+        u64 pos = lower_bound_hdr(O, nO, h);
+        bool inner = pos < nO && (O[pos] & SA_HDR_MASK) == h;
+        u64 r = inner ? O[pos] : 0;
+        u64 pos2 = pos + (inner ? 1 : 0);
+        bool has_adj = pos2 < nO && (O[pos2] & SA_HDR_MASK) == h + SA_ONE_BLOCK;
+        u64 r2 = has_adj ? O[pos2] : 0;
+        bool am = has_adj && (x & SA_BIT17) && (r2 & 1ull);
+        if (inner) {
+            u32 c;
+            u64 word;
+            inner_calc(x, r, same, CONT_RHS, c, word);
+            e.cnt += c;
+            if (CONT_RHS) {
+                // the rhs word at h may also end a cross-word match that started in lhs[i-1]
+                if (i > 0) {
+                    u64 lp = D[i - 1];
+                    if ((lp & SA_HDR_MASK) + SA_ONE_BLOCK == h && (lp & SA_BIT17) && (r & 1ull)) word |= 1ull;
+                }
+            } else if (am) {
+                word |= SA_BIT17;
+            }
+            e.w0 = word;
+            e.n_emit = 1;
+            e.inner = true;
+            e.diff = (x != r);
+        }
+        if (am) {
+            e.cnt += 1;
+            if (CONT_RHS) {
+                // adjacent-only continuation, unless lhs[i+1] pairs with that rhs word itself
+                bool next_handles = (i + 1 < nD) && ((D[i + 1] & SA_HDR_MASK) == h + SA_ONE_BLOCK);
+                if (!next_handles) {
+                    u64 w = (r2 & SA_HDR_MASK) | 1ull;
+                    if (e.n_emit == 0) e.w0 = w; else e.w1 = w;
+                    e.n_emit++;
+                }
+            } else if (!inner) {
+                e.w0 = h | SA_BIT17;
+                e.n_emit = 1;
+            }
+        }
+        e.entry = inner || am;
+    } else {
+        // x is an rhs word: partners are lhs words at header h - 1 block (adjacent) and h (inner)
+        const bool can_adj = h >= SA_ONE_BLOCK;
+        u64 pos = lower_bound_hdr(O, nO, can_adj ? h - SA_ONE_BLOCK : h);
+        bool has_adj = can_adj && pos < nO && (O[pos] & SA_HDR_MASK) == h - SA_ONE_BLOCK;
+        u64 lp = has_adj ? O[pos] : 0;
+        u64 posl = pos + (has_adj ? 1 : 0);
+        bool inner = posl < nO && (O[posl] & SA_HDR_MASK) == h;
+        u64 l = inner ? O[posl] : 0;
+        bool am = has_adj && (lp & SA_BIT17) && (x & 1ull);
+        if (!CONT_RHS && am) {
+            // adjacent-only continuation on the lhs side, unless rhs[i-1] pairs with lp itself
+            bool prev_handles = (i > 0) && ((D[i - 1] & SA_HDR_MASK) == h - SA_ONE_BLOCK);
+            if (!prev_handles) {
+                e.w0 = (lp & SA_HDR_MASK) | SA_BIT17;
+                e.n_emit = 1;
+            }
+        }
+        if (inner) {
+            u32 c;
+            u64 word;
+            inner_calc(l, x, same, CONT_RHS, c, word);
+            e.cnt += c;
+            if (CONT_RHS) {
+                if (am) word |= 1ull;
+            } else if (i + 1 < nD) {
+                u64 rn = D[i + 1];
+                if ((rn & SA_HDR_MASK) == h + SA_ONE_BLOCK && (l & SA_BIT17) && (rn & 1ull)) word |= SA_BIT17;
+            }
+            if (e.n_emit == 0) e.w0 = word; else e.w1 = word;
+            e.n_emit++;
+            e.inner = true;
+            e.diff = (l != x);
+            e.doc = (u32)(l >> SA_KEY_SHIFT);
+        } else if (am) {
+            if (CONT_RHS) {
+                e.w0 = h | 1ull;
+                e.n_emit = 1;
+            }
+            e.doc = (u32)(lp >> SA_KEY_SHIFT);
+        }
+        if (am) e.cnt += 1;
+        e.entry = inner || am;
+    }
+    return e;
+}
+
+struct StepShared {
+    u32 warp_sums[PT / 32];
+    u32 edoc[PT];
+    u32 ecnt[PT];
+    u32 carry_doc, carry_cnt, carry_valid;
+    u32 st_inner, st_diff;
+    u64 n_cont, n_docs;
+};
+
+// exclusive block scan (all PT threads call); returns the exclusive prefix, `total` = block sum
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *warp_sums, u32 &total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                 // protect warp_sums from the previous use
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    u32 base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PT / 32; w++) {
+        u32 s = warp_sums[w];
+        if (w < (int)warp) base += s;
+        tot += s;
+    }
+    total = tot;
+    return base + incl - v;
+}
+
+// One bigram step over this CTA's chunk.  Writes the continuation list (sorted) to cont_out and
+// the per-doc counts (doc << 32 | count, sorted by doc, zero counts kept) to docs_out.
+template <bool CONT_RHS, bool DRIVER_LHS>
+__device__ void bigram_step(const u64 *__restrict__ D, u64 nD, const u64 *__restrict__ O, u64 nO, bool same,
+                            u64 *__restrict__ cont_out, u64 *__restrict__ docs_out, StepShared &S) {
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        S.n_cont = 0;
+        S.n_docs = 0;
+        S.carry_valid = 0;
+        S.st_inner = 0;
+        S.st_diff = 0;
+    }
+    __syncthreads();
+    for (u64 t0 = 0; t0 < nD; t0 += PT) {
+        const u64 i = t0 + tid;
+        Elem e;
+        e.n_emit = 0;
+        e.entry = e.inner = e.diff = false;
+        e.cnt = 0;
+        e.doc = 0;
+        e.w0 = e.w1 = 0;
+        if (i < nD) e = compute_elem<CONT_RHS, DRIVER_LHS>(D, nD, i, O, nO, same);
+        // speculation bookkeeping
+        unsigned mi = __ballot_sync(0xffffffffu, e.inner), md = __ballot_sync(0xffffffffu, e.diff);
+        if ((tid & 31) == 0 && mi) {
+            atomicAdd(&S.st_inner, (u32)__popc(mi));
+            if (md) atomicAdd(&S.st_diff, (u32)__popc(md));
+        }
+        // continuation words, in order
+        u32 total;
+        u32 off = block_excl_scan(e.n_emit, S.warp_sums, total);
+        const u64 cbase = S.n_cont;
+        if (e.n_emit >= 1) cont_out[cbase + off] = e.w0;
+        if (e.n_emit == 2) cont_out[cbase + off + 1] = e.w1;
+        // (doc, count) entries of this tile, compacted into shared memory
+        u32 etotal;
+        u32 eoff = block_excl_scan(e.entry ? 1u : 0u, S.warp_sums, etotal);
+        if (e.entry) {
+            S.edoc[eoff] = e.doc;
+            S.ecnt[eoff] = e.cnt;
+        }
+        __syncthreads();
+        if (tid == 0) S.n_cont = cbase + total;
+        if (etotal) {     // block-uniform
+            const bool flush = S.carry_valid && S.edoc[0] != S.carry_doc;
+            const bool merge = S.carry_valid && S.edoc[0] == S.carry_doc;
+            const u32 c_doc = S.carry_doc, c_cnt = S.carry_cnt;
+            const u64 dbase = S.n_docs;
+            // segmented sum: the head of each run adds up its run
+            bool emit = false, is_last = false;
+            u32 sum = 0, doc = 0;
+            if (tid < etotal) {
+                doc = S.edoc[tid];
+                bool head = (tid == 0) || (S.edoc[tid - 1] != doc);
+                if (head) {
+                    u32 k = tid;
+                    while (k < etotal && S.edoc[k] == doc) sum += S.ecnt[k++];
+                    if (tid == 0 && merge) sum += c_cnt;
+                    is_last = (k == etotal);
+                    emit = !is_last;
+                }
+            }
+            u32 htotal;
+            u32 hoff = block_excl_scan(emit ? 1u : 0u, S.warp_sums, htotal);
+            const u64 obase = dbase + (flush ? 1 : 0);
+            if (emit) docs_out[obase + hoff] = ((u64)doc << 32) | sum;
+            if (tid == 0 && flush) docs_out[dbase] = ((u64)c_doc << 32) | c_cnt;
+            __syncthreads();
+            if (is_last) {            // exactly one thread: the head of the tile's last run
+                S.carry_doc = doc;
+                S.carry_cnt = sum;
+                S.carry_valid = 1;
+                S.n_docs = obase + htotal;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && S.carry_valid) {
+        docs_out[S.n_docs] = ((u64)S.carry_doc << 32) | S.carry_cnt;
+        S.n_docs += 1;
+        S.carry_valid = 0;
+    }
+    __syncthreads();
+}
+
+// cur[i].count = min(cur[i].count, prev[doc].count) (0 if the doc is not in prev)
+// == _intersect_bigram_matches (middle_out.py:73-93) on nested / sorted doc lists.
+__device__ void and_min(u64 *__restrict__ cur, u64 n_cur, const u64 *__restrict__ prev, u64 n_prev) {
+    for (u64 i = threadIdx.x; i < n_cur; i += PT) {
+        u64 e = cur[i];
+        u64 doc = e >> 32;
+        u64 lo = 0, hi = n_prev;
+        while (lo < hi) {
+            u64 mid = (lo + hi) >> 1;
+            if ((prev[mid] >> 32) < doc) lo = mid + 1; else hi = mid;
+        }
+        u32 c = 0;
+        if (lo < n_prev && (prev[lo] >> 32) == doc) c = min((u32)(prev[lo] & 0xFFFFFFFFull), (u32)(e & 0xFFFFFFFFull));
+        cur[i] = (doc << 32) | c;
+    }
+    __syncthreads();
+}
+
+struct ChainResult { u64 *docs; u64 n_docs; u64 *cont; u64 n_cont; };
+
+__global__ void __launch_bounds__(PT)
+phrase_kernel(const PhraseArgs a) {
+    __shared__ StepShared S;
+    __shared__ u64 s_lo[SA_MAX_PHRASE_TERMS], s_n[SA_MAX_PHRASE_TERMS];
+    __shared__ u64 s_slab;
+    __shared__ int s_ok;
+
+    const u32 q = blockIdx.y;
+    const PhraseQuery &pq = a.queries[q];
+    const u32 n_terms = pq.n_terms;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 d0 = a.doc_base + (u64)blockIdx.x * a.docs_per_chunk;
+    const u64 dend = a.doc_base + a.n_docs;
+    if (d0 >= dend) return;
+    const u64 d1 = min(d0 + a.docs_per_chunk, dend);
+
+    // 1. every term's slice for this doc range
+    for (u32 t = warp; t < n_terms; t += PT / 32) {
+        const u64 *lst = a.words + pq.off[t];
+        u64 lo = warp_lower_bound_shifted(lst, 0, pq.len[t], d0, SA_KEY_SHIFT);
+        u64 hi = warp_lower_bound_shifted(lst, lo, pq.len[t], d1, SA_KEY_SHIFT);
+        if (lane == 0) { s_lo[t] = lo; s_n[t] = hi - lo; }
+    }
+    __syncthreads();
+    u64 cap = 0, widest = 0;
+    for (u32 t = 0; t < n_terms; t++) {
+        cap = max(cap, s_n[t]);
+        if (s_n[t]) widest++;
+    }
+    // A chunk where fewer than two terms occur has no pairs at any step.  (A chunk that merely
+    // misses ONE term must still run its earlier steps: their pairs count towards the global
+    // same-term decision of the reference.)
+    if (widest < 2) return;
+    cap += 2;
+
+    // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers
+    if (tid == 0) {
+        unsigned long long need = 6ull * cap;
+        unsigned long long at = atomicAdd(a.arena_used, need);
+        s_ok = (at + need <= a.arena_cap);
+        s_slab = at;
+        if (!s_ok) atomicExch(&a.stats[q].overflow, 1u);
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    u64 *contA = a.arena + s_slab, *contB = contA + cap;
+    u64 *docsA = contB + cap, *docsB = docsA + cap, *docsL = docsB + cap, *docsR = docsL + cap;
+
+    auto slice = [&](u32 t) { return a.words + pq.off[t] + s_lo[t]; };
+
+    // Runs one chain over terms [ta, tb).  lr: left-to-right (cont = RHS) else right-to-left.
+    auto run_chain = [&](u32 ta, u32 tb, bool lr, u64 *final_docs) -> ChainResult {
+        ChainResult res;
+        res.docs = final_docs;
+        res.n_docs = 0;
+        res.cont = contA;
+        res.n_cont = 0;
+        const u64 *carry = lr ? slice(ta) : slice(tb - 1);
+        u64 n_carry = lr ? s_n[ta] : s_n[tb - 1];
+        u64 *cont_bufs[2] = {contA, contB};
+        u64 *doc_bufs[2] = {docsA, docsB};
+        int flip = 0;
+        const u64 *prev_docs = nullptr;
+        u64 n_prev = 0;
+        const u32 n_steps = tb - ta - 1;
+        for (u32 s = 0; s < n_steps; s++) {
+            const u32 tnew = lr ? (ta + 1 + s) : (tb - 2 - s);     // also the step id
+            const bool same = (pq.same_guess >> tnew) & 1u;
+            const u64 *other = slice(tnew);
+            const u64 n_other = s_n[tnew];
+            if (n_carry == 0 || n_other == 0) {   // no pairs from here on in this doc range
+                res.n_docs = 0;
+                res.n_cont = 0;
+                break;
+            }
+            u64 *cont_out = cont_bufs[flip];
+            u64 *docs_out = (s == n_steps - 1) ? final_docs : doc_bufs[flip];
+            // the first step may drive from the shorter side; later steps drive from the carry
+            const bool drive_carry = (s > 0) || (n_carry <= n_other);
+            if (lr) {
+                if (drive_carry) bigram_step<true, true>(carry, n_carry, other, n_other, same, cont_out, docs_out, S);
+                else bigram_step<true, false>(other, n_other, carry, n_carry, same, cont_out, docs_out, S);
+            } else {
+                if (drive_carry) bigram_step<false, false>(carry, n_carry, other, n_other, same, cont_out, docs_out, S);
+                else bigram_step<false, true>(other, n_other, carry, n_carry, same, cont_out, docs_out, S);
+            }
+            const u64 n_cont = S.n_cont, n_docs = S.n_docs;
+            if (tid == 0) {
+                if (S.st_inner) atomicAdd(&a.stats[q].n_inner[tnew], S.st_inner);
+                if (S.st_diff) atomicAdd(&a.stats[q].n_diff[tnew], S.st_diff);
+            }
+            __syncthreads();
+            if (prev_docs) and_min(docs_out, n_docs, prev_docs, n_prev);
+            prev_docs = docs_out;
+            n_prev = n_docs;
+            carry = cont_out;
+            n_carry = n_cont;
+            res.docs = docs_out;
+            res.n_docs = n_docs;
+            res.cont = cont_out;
+            res.n_cont = n_cont;
+            flip ^= 1;
+            if (n_docs == 0) {       // nothing can survive the remaining steps
+                res.n_docs = 0;
+                break;
+            }
+        }
+        return res;
+    };
+
+    ChainResult fin;
+    if (pq.mode == SA_PHRASE_MODE_LR) {
+        fin = run_chain(0, n_terms, true, docsL);
+    } else if (pq.mode == SA_PHRASE_MODE_RL) {
+        fin = run_chain(0, n_terms, false, docsL);
+    } else {
+        // both chains always run (their pair statistics feed the speculation check)
+        ChainResult left = run_chain(0, pq.split, true, docsL);
+        fin = run_chain(pq.split, n_terms, false, docsR);
+        if (left.n_docs == 0) fin.n_docs = 0;
+        and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
+    }
+
+    // optional dump for the per-op parity export (single chunk)
+    if (a.dump.cont) {
+        for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
+        for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
+        if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
+    }
+
+    // 3. scatter the matches into the dense vector (phrase_freqs[ids] = counts, middle_out.py:441)
+    float *out = a.out + (u64)q * a.out_stride;
+    Bm25Params p = a.bm25;
+    p.idf = pq.idf;
+    for (u64 i = tid; i < fin.n_docs; i += PT) {
+        u64 e = fin.docs[i];
+        u32 c = (u32)(e & 0xFFFFFFFFull);
+        if (c == 0) continue;
+        u64 d = (e >> 32) - a.doc_base;
+        if (d >= a.n_docs) continue;
+        out[d] = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+    }
+}
+
+int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries) {
+    if (n_queries == 0 || a.n_docs == 0) return SA_OK;
+    dim3 grid(a.n_chunks, n_queries);
+    KernelTimer t(ix, 2);
+    phrase_kernel<<<grid, PT, 0, ix->stream>>>(a);
+    SA_CUDA(cudaGetLastError());
+    t.stop();
+    ix->stats.phrase_kernel_launches++;
+    ix->stats.total_launches++;
+    return SA_OK;
+}
+
+// ------------------------------------------------------------------------------- host side
+// BM25 over every doc (bm25.pyx:20-25) for parameter sets where tf == 0 does not score +0.0.
+__global__ void bm25_dense_kernel(float *__restrict__ tf, const float *__restrict__ dl, u64 n, Bm25Params p) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tf[i] = bm25_one(tf[i], dl[i], p);
+}
+
+static u64 padded(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
+
+// direction / speculation plan exactly as compute_phrase_freqs picks it (middle_out.py:154-168)
+static void plan_phrase(PhraseQuery &pq, const u32 *term_ids) {
+    const u32 n = pq.n_terms;
+    u32 shortest = 0;
+    for (u32 i = 1; i < n; i++) if (pq.len[i] < pq.len[shortest]) shortest = i;   // first minimum
+    pq.same_guess = 0;
+    if (shortest <= 1) {
+        pq.mode = SA_PHRASE_MODE_LR;
+        if (term_ids[0] == term_ids[1]) pq.same_guess |= 1u << 1;
+    } else if (shortest >= n - 2) {
+        pq.mode = SA_PHRASE_MODE_RL;
+        if (term_ids[n - 2] == term_ids[n - 1]) pq.same_guess |= 1u << (n - 2);
+    } else {
+        pq.mode = SA_PHRASE_MODE_MID;
+        pq.split = shortest;
+        if (term_ids[0] == term_ids[1]) pq.same_guess |= 1u << 1;
+        if (term_ids[n - 2] == term_ids[n - 1]) pq.same_guess |= 1u << (n - 2);
+    }
+}
+
+// order in which the steps of a plan run (for verifying the speculation)
+static void step_order(const PhraseQuery &pq, std::vector<u32> &order) {
+    order.clear();
+    const u32 n = pq.n_terms;
+    if (pq.mode == SA_PHRASE_MODE_LR) for (u32 s = 1; s < n; s++) order.push_back(s);
+    else if (pq.mode == SA_PHRASE_MODE_RL) for (int s = (int)n - 2; s >= 0; s--) order.push_back((u32)s);
+    else {
+        for (u32 s = 1; s < pq.split; s++) order.push_back(s);
+        for (int s = (int)n - 2; s >= (int)pq.split; s--) order.push_back((u32)s);
+    }
+}
+
+// Runs phrase queries (already planned) into ix->dense; loops until the same-term speculation
+// of every query is confirmed.  lists may live in ix->d_words (off = absolute word offsets).
+static int run_phrase_queries(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
+                              int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump) {
+    const u32 Q = (u32)pqs.size();
+    const u64 stride = padded(ix->n_docs);
+    int rc;
+    if ((rc = ix->dense.reserve((size_t)Q * stride * sizeof(float)))) return rc;
+    if ((rc = ix->queries.reserve((size_t)Q * sizeof(PhraseQuery)))) return rc;
+    if ((rc = ix->cand_meta.reserve((size_t)Q * sizeof(PhraseStats) + 64))) return rc;
+    // scratch arena: per query <= 6 * (sum of list lengths + 2 per chunk)
+    u32 n_chunks = n_chunks_hint;
+    if (n_chunks == 0) {
+        u64 want = std::max<u64>(1, (u64)ix->num_sms * 8 / std::max<u32>(Q, 1));
+        n_chunks = (u32)std::min<u64>(want, std::max<u64>(1, ix->n_docs / 512));
+        n_chunks = std::max<u32>(n_chunks, 1);
+    }
+    const u64 docs_per_chunk = (ix->n_docs + n_chunks - 1) / n_chunks;
+    u64 arena_words = 64;
+    for (auto &pq : pqs) {
+        u64 sum = 0;
+        for (u32 t = 0; t < pq.n_terms; t++) sum += pq.len[t];
+        arena_words += 6 * (sum + 2ull * n_chunks);
+    }
+    if ((rc = ix->phrase_scratch.reserve(arena_words * sizeof(u64) + 64))) return rc;
+    unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
+    u64 *d_arena = (u64 *)ix->phrase_scratch.p + 8;
+    PhraseStats *d_stats = (PhraseStats *)ix->cand_meta.p;
+    std::vector<PhraseStats> h_stats(Q);
+    std::vector<u32> order;
+
+    for (int attempt = 0; attempt < (int)SA_MAX_PHRASE_TERMS + 2; attempt++) {
+        SA_CUDA(cudaMemcpyAsync(ix->queries.p, pqs.data(), (size_t)Q * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
+        SA_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)Q * sizeof(PhraseStats), ix->stream));
+        SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
+        SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, (size_t)Q * stride * sizeof(float), ix->stream));
+        PhraseArgs a;
+        memset(&a, 0, sizeof(a));
+        a.words = d_words;
+        a.doc_lens = ix->d_doc_lens;
+        a.n_docs = ix->n_docs;
+        a.doc_base = ix->doc_base;
+        a.queries = ix->queries.as<PhraseQuery>();
+        a.stats = d_stats;
+        a.out = ix->dense.as<float>();
+        a.out_stride = stride;
+        a.n_chunks = n_chunks;
+        a.docs_per_chunk = docs_per_chunk;
+        a.arena = d_arena;
+        a.arena_used = d_used;
+        a.arena_cap = arena_words;
+        a.bm25 = p;
+        a.score = score;
+        a.dump = dump;
+        if ((rc = launch_phrase(ix, a, Q))) return rc;
+        SA_CUDA(cudaMemcpyAsync(h_stats.data(), d_stats, (size_t)Q * sizeof(PhraseStats), cudaMemcpyDeviceToHost, ix->stream));
+        SA_CUDA(cudaStreamSynchronize(ix->stream));
+        bool again = false;
+        for (u32 q = 0; q < Q; q++) {
+            SA_CHECK(!h_stats[q].overflow, "phrase scratch arena exhausted (internal sizing error)");
+            step_order(pqs[q], order);
+            for (u32 s : order) {
+                bool actual = h_stats[q].n_inner[s] > 0 && h_stats[q].n_diff[s] == 0;
+                bool guess = (pqs[q].same_guess >> s) & 1u;
+                if (actual != guess) {      // later steps ran on a wrong premise: fix this one, redo
+                    pqs[q].same_guess ^= 1u << s;
+                    again = true;
+                    break;
+                }
+            }
+        }
+        if (!again) return SA_OK;
+    }
+    sa_set_error("same-term speculation did not converge");
+    return SA_ERR_ARG;
+}
+
+static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
+                         int score, float idf, float avg_doc_len, float k1, float b,
+                         uint64_t min_payload, uint64_t max_payload, float *out_host) {
+    SA_CHECK(ix && term_ids && out_host, "NULL argument");
+    SA_CHECK(n_terms >= 2, "Must have at least two terms");
+    SA_CHECK(n_terms <= SA_MAX_PHRASE_TERMS, "phrases longer than %d terms are not supported", SA_MAX_PHRASE_TERMS);
+    SA_CHECK(slop == 0, "slop > 0 is not implemented yet");
+    SA_CHECK(min_payload == 0 && max_payload == SA_ALL_BITS, "min_posn/max_posn on phrases is not implemented yet");
+    SA_CHECK(ix->n_rows == 0, "phrase search on a sliced array is not implemented yet");
+    std::lock_guard<std::mutex> g(ix->mu);
+    SA_CUDA(cudaSetDevice(ix->device));
+    if (ix->n_docs == 0) return SA_OK;
+    bool missing = false;
+    for (u32 i = 0; i < n_terms; i++) {
+        SA_CHECK(term_ids[i] == SA_NO_TERM || term_ids[i] < ix->n_terms, "term id %u out of range", term_ids[i]);
+        if (term_ids[i] == SA_NO_TERM || ix->h_len[term_ids[i]] == 0) missing = true;
+    }
+    if (missing || (score && avg_doc_len == 0.0f)) {
+        // unknown term inside a phrase -> zeros (postings.py:705-708); with tf == 0 everywhere BM25
+        // still runs over all docs in the reference, which only matters for exotic parameters
+        memset(out_host, 0, ix->n_docs * sizeof(float));
+        if (!(score && avg_doc_len != 0.0f)) return SA_OK;
+    }
+    Bm25Params p;
+    p.idf = idf; p.avg_doc_len = avg_doc_len; p.k1 = k1; p.b = b; p.one_minus_b = 1 - b;
+    p.sparse_ok = (ix->doc_lens_nonneg && k1 > 0.0f && std::isfinite(k1) && b >= 0.0f && b < 1.0f &&
+                   avg_doc_len > 0.0f && std::isfinite(avg_doc_len) && std::isfinite(idf) && idf >= 0.0f &&
+                   !std::signbit(idf)) ? 1 : 0;
+    const u64 stride = padded(ix->n_docs);
+    int rc;
+    if (!missing) {
+        std::vector<PhraseQuery> pqs(1);
+        PhraseQuery &pq = pqs[0];
+        memset(&pq, 0, sizeof(pq));
+        pq.n_terms = n_terms;
+        pq.idf = idf;
+        for (u32 i = 0; i < n_terms; i++) {
+            pq.off[i] = ix->h_off[term_ids[i]];
+            pq.len[i] = ix->h_len[term_ids[i]];
+        }
+        plan_phrase(pq, term_ids);
+        PhraseDump nodump;
+        memset(&nodump, 0, sizeof(nodump));
+        // raw counts first when BM25 must touch every doc
+        if ((rc = run_phrase_queries(ix, pqs, ix->d_words, score && p.sparse_ok, p, 0, nodump))) return rc;
+    } else {
+        if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
+        SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, stride * sizeof(float), ix->stream));
+    }
+    if (score && !p.sparse_ok) {
+        unsigned blocks = (unsigned)((ix->n_docs + 255) / 256);
+        bm25_dense_kernel<<<blocks, 256, 0, ix->stream>>>(ix->dense.as<float>(), ix->d_doc_lens, ix->n_docs, p);
+        SA_CUDA(cudaGetLastError());
+        ix->stats.total_launches++;
+    }
+    SA_CUDA(cudaMemcpyAsync(out_host, ix->dense.p, ix->n_docs * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+extern "C" int sa_phrase_freqs(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
+                               uint64_t min_payload, uint64_t max_payload, float *out_host) {
+    return phrase_common(ix, term_ids, n_terms, slop, 0, 0.0f, 1.0f, 1.0f, 0.0f, min_payload, max_payload, out_host);
+}
+
+extern "C" int sa_score_phrase(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
+                               float idf, float avg_doc_len, float k1, float b,
+                               uint64_t min_payload, uint64_t max_payload, float *out_host) {
+    return phrase_common(ix, term_ids, n_terms, slop, 1, idf, avg_doc_len, k1, b, min_payload, max_payload, out_host);
+}
+
+// ---------------------------------------------------------------- per-op parity exports
+extern "C" int sa_op_bigram_freqs(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                                  int cont_rhs, int device,
+                                  uint64_t *ids_out, float *counts_out, uint64_t *n_ids_out,
+                                  uint64_t *next_out, uint64_t *n_next_out) {
+    SA_CHECK(ids_out && counts_out && n_ids_out && next_out && n_next_out, "NULL argument");
+    *n_ids_out = 0;
+    *n_next_out = 0;
+    if (n_lhs == 0 || n_rhs == 0) return SA_OK;
+    SA_CHECK(lhs && rhs, "NULL argument");
+    // a throw-away two-term index over one shard that covers every doc id present
+    std::vector<u64> words(lhs, lhs + n_lhs);
+    words.insert(words.end(), rhs, rhs + n_rhs);
+    u64 max_doc = std::max(lhs[n_lhs - 1], rhs[n_rhs - 1]) >> SA_KEY_SHIFT;
+    std::vector<float> dl(max_doc + 1, 1.0f);
+    u64 offs[2] = {0, n_lhs}, lens[2] = {n_lhs, n_rhs};
+    sa_index *ix = nullptr;
+    int rc = sa_index_create(words.data(), words.size(), offs, lens, 2, dl.data(), max_doc + 1, 0, device, &ix);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> g(ix->mu);
+        std::vector<PhraseQuery> pqs(1);
+        PhraseQuery &pq = pqs[0];
+        memset(&pq, 0, sizeof(pq));
+        pq.n_terms = 2;
+        pq.off[0] = 0; pq.len[0] = n_lhs;
+        pq.off[1] = n_lhs; pq.len[1] = n_rhs;
+        pq.mode = cont_rhs ? SA_PHRASE_MODE_LR : SA_PHRASE_MODE_RL;
+        pq.same_guess = 0;
+        const u64 cap = 2 * std::min(n_lhs, n_rhs) + std::max(n_lhs, n_rhs) + 8;
+        DevBuf dbuf;
+        rc = dbuf.reserve((2 * cap + 2) * sizeof(u64));
+        if (!rc) {
+            PhraseDump dump;
+            dump.cont = dbuf.as<u64>();
+            dump.docs = dump.cont + cap;
+            dump.n_cont = dump.docs + cap;
+            dump.n_docs = dump.n_cont + 1;
+            cudaMemsetAsync(dump.n_cont, 0, 2 * sizeof(u64), ix->stream);
+            Bm25Params p;
+            memset(&p, 0, sizeof(p));
+            rc = run_phrase_queries(ix, pqs, ix->d_words, 0, p, 1, dump);
+            if (!rc) {
+                u64 n[2];
+                cudaMemcpy(n, dump.n_cont, 2 * sizeof(u64), cudaMemcpyDeviceToHost);
+                std::vector<u64> docs(n[1]);
+                cudaMemcpy(next_out, dump.cont, n[0] * sizeof(u64), cudaMemcpyDeviceToHost);
+                if (n[1]) cudaMemcpy(docs.data(), dump.docs, n[1] * sizeof(u64), cudaMemcpyDeviceToHost);
+                for (u64 i = 0; i < n[1]; i++) {
+                    ids_out[i] = docs[i] >> 32;
+                    counts_out[i] = (float)(u32)(docs[i] & 0xFFFFFFFFull);
+                }
+                *n_next_out = n[0];
+                *n_ids_out = n[1];
+            }
+        }
+        dbuf.release();
+    }
+    sa_index_destroy(ix);
+    return rc;
+}
+
+// popcount64_reduce / as_dense / bm25_score on raw arrays: the term kernel on a one-term index
+extern "C" int sa_op_popcount64_reduce(const uint64_t *words, uint64_t n, int device,
+                                       uint64_t *keys_out, float *counts_out, uint64_t *n_out) {
+    SA_CHECK(keys_out && counts_out && n_out, "NULL argument");
+    *n_out = 0;
+    if (n == 0) return SA_OK;
+    SA_CHECK(words, "NULL argument");
+    u64 min_doc = words[0] >> SA_KEY_SHIFT, max_doc = words[n - 1] >> SA_KEY_SHIFT;
+    u64 nd = max_doc - min_doc + 1;
+    std::vector<float> dl(nd, 1.0f), tf(nd);
+    u64 off = 0, len = n;
+    sa_index *ix = nullptr;
+    int rc = sa_index_create(words, n, &off, &len, 1, dl.data(), nd, min_doc, device, &ix);
+    if (rc) return rc;
+    rc = sa_termfreqs(ix, 0, 0, SA_ALL_BITS, tf.data());
+    sa_index_destroy(ix);
+    if (rc) return rc;
+    // docs present in the list keep their (possibly zero) count: walk the keys on the host
+    u64 m = 0, last = ~0ull;
+    for (u64 i = 0; i < n; i++) {
+        u64 d = words[i] >> SA_KEY_SHIFT;
+        if (d != last) { keys_out[m] = d; counts_out[m] = tf[d - min_doc]; m++; last = d; }
+    }
+    *n_out = m;
+    return SA_OK;
+}
+
+extern "C" int sa_op_bm25_score(float *tf_inout, const float *doc_lens, uint64_t n, float avg_doc_len,
+                                float idf, float k1, float b, int device) {
+    if (n == 0) return SA_OK;
+    SA_CHECK(tf_inout && doc_lens, "NULL argument");
+    SA_CUDA(cudaSetDevice(device));
+    float *d_tf = nullptr, *d_dl = nullptr;
+    SA_CUDA(cudaMalloc(&d_tf, n * sizeof(float)));
+    if (cudaMalloc(&d_dl, n * sizeof(float)) != cudaSuccess) { cudaFree(d_tf); sa_set_error("cudaMalloc failed"); return SA_ERR_NOMEM; }
+    cudaMemcpy(d_tf, tf_inout, n * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_dl, doc_lens, n * sizeof(float), cudaMemcpyHostToDevice);
+    Bm25Params p;
+    p.idf = idf; p.avg_doc_len = avg_doc_len; p.k1 = k1; p.b = b; p.one_minus_b = 1 - b; p.sparse_ok = 0;
+    bm25_dense_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_tf, d_dl, n, p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(tf_inout, d_tf, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_tf);
+    cudaFree(d_dl);
+    if (e != cudaSuccess) { sa_set_error("sa_op_bm25_score: %s", cudaGetErrorString(e)); return SA_ERR_CUDA; }
+    return SA_OK;
+}
+
+// ------------------------------------------------------ sliced arrays (not implemented yet)
+extern "C" int sa_index_set_rows(sa_index *ix, const uint64_t *rows, uint64_t n_rows) {
+    SA_CHECK(ix, "index is NULL");
+    if (rows == nullptr && n_rows == 0) { ix->n_rows = 0; return SA_OK; }
+    sa_set_error("sa_index_set_rows: sliced arrays are not implemented yet");
+    return SA_ERR_ARG;
+}
+
+extern "C" int sa_docfreq_rows(sa_index *, uint32_t, uint64_t *) {
+    sa_set_error("sa_docfreq_rows: sliced arrays are not implemented yet");
+    return SA_ERR_ARG;
+}
