@@ -83,10 +83,13 @@ struct Bm25Params {
 };
 
 // A query against one shard, as the kernels see it.
+#define SA_NO_DIR 0xFFFFFFFFFFFFFFFFull
 struct TermQuery {
     u64 word_off;      // offset of the term's first word in d_words
     u64 n_words;       // 0 => unknown term (zeros)
+    u64 dir_off;       // offset of the term's tile directory in d_tile_dir, or SA_NO_DIR
     float idf;
+    u32 pad;
 };
 
 // ---- the index handle ---------------------------------------------------------------
@@ -103,6 +106,15 @@ struct sa_index {
     u64 *d_words = nullptr;          // [n_words + 1] (one readable pad word)
     float *d_doc_lens = nullptr;     // [n_docs]
     u32 *d_df = nullptr;             // [n_terms] distinct docs per term (this shard)
+    // tile directory of long posting lists: for term t with h_dir_off[t] != SA_NO_DIR,
+    // d_tile_dir[h_dir_off[t] + j] = index (within the term's list) of the first word whose
+    // doc lies in tile >= j, j = 0..n_tiles  (tile = 4096 docs).  Built on the device at upload.
+    u32 *d_tile_dir = nullptr;
+    std::vector<u64> h_dir_off;
+    // per-doc BM25 length norm k1*((1-b)+b*dl/avgdl) for the last used (k1, b, avgdl)
+    float *d_norm = nullptr;         // [padded n_docs]
+    float norm_k1 = 0, norm_b = 0, norm_avgdl = 0;
+    bool norm_valid = false;
     // host mirrors for query set-up
     std::vector<u64> h_off, h_len;
     std::vector<u32> h_df;

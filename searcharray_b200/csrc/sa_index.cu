@@ -67,6 +67,35 @@ __global__ void df_kernel(const u64 *__restrict__ words, u64 n_words,
     if (head) atomicAdd(&df[term_of_slot[lo]], 1u);
 }
 
+// Tile directory of a long posting list: dir[j] = index (within the list) of the first word whose
+// doc falls in tile >= j, for j = 0..n_tiles.  One thread per word fills the entries it starts.
+__global__ void tile_dir_kernel(const u64 *__restrict__ words, u64 n_words,
+                                const u64 *__restrict__ term_off_sorted, const u64 *__restrict__ slot_len,
+                                const u64 *__restrict__ slot_dir_off, u32 n_slots,
+                                u32 *__restrict__ dir, u64 doc_base, u32 n_tiles) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    u32 lo = 0, hi = n_slots;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (term_off_sorted[mid] <= i) lo = mid; else hi = mid;
+    }
+    const u64 doff = slot_dir_off[lo];
+    if (doff == SA_NO_DIR) return;
+    const u64 start = term_off_sorted[lo], len = slot_len[lo];
+    const u32 local = (u32)(i - start);
+    u32 *d = dir + doff;
+    const u32 t_i = (u32)(((words[i] >> SA_KEY_SHIFT) - doc_base) / SA_TILE_DOCS);
+    if (local == 0) {
+        for (u32 t = 0; t <= t_i && t <= n_tiles; t++) d[t] = 0;
+    } else {
+        const u32 t_p = (u32)(((words[i - 1] >> SA_KEY_SHIFT) - doc_base) / SA_TILE_DOCS);
+        for (u32 t = t_p + 1; t <= t_i && t <= n_tiles; t++) d[t] = local;
+    }
+    if (local == len - 1)
+        for (u32 t = t_i + 1; t <= n_tiles; t++) d[t] = (u32)len;
+}
+
 extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
                                const uint64_t *term_offsets, const uint64_t *term_lengths, uint32_t n_terms,
                                const float *doc_lens, uint64_t n_docs, uint64_t doc_base,
@@ -92,6 +121,7 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
     ix->h_off.assign(term_offsets, term_offsets + n_terms);
     ix->h_len.assign(term_lengths, term_lengths + n_terms);
     ix->h_df.assign(n_terms, 0);
+    ix->h_dir_off.assign(n_terms, SA_NO_DIR);
 
 #define CREATE_CUDA(call)                                                              \
     do {                                                                               \
@@ -146,6 +176,20 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
         u64 *d_off = nullptr;
         u32 *d_slot = nullptr;
         u32 n_slots = (u32)off_sorted.size();
+        // tile directories for long lists (short ones are searched: they stay cache resident)
+        const u32 n_tiles = (u32)((n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+        const u64 dir_min_words = std::max<u64>(1024, n_tiles / 2);
+        std::vector<u64> slot_len(n_slots), slot_dir(n_slots, SA_NO_DIR);
+        u64 dir_words = 0;
+        for (u32 sI = 0; sI < n_slots; sI++) {
+            u32 t = term_of_slot[sI];
+            slot_len[sI] = term_lengths[t];
+            if (term_lengths[t] >= dir_min_words && term_lengths[t] < 0xFFFFFFFFull) {
+                slot_dir[sI] = dir_words;
+                ix->h_dir_off[t] = dir_words;
+                dir_words += (u64)n_tiles + 1;
+            }
+        }
         CREATE_CUDA(cudaMalloc(&d_off, n_slots * sizeof(u64)));
         CREATE_CUDA(cudaMalloc(&d_slot, n_slots * sizeof(u32)));
         CREATE_CUDA(cudaMemcpyAsync(d_off, off_sorted.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
@@ -155,9 +199,24 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
         CREATE_CUDA(cudaGetLastError());
         ix->stats.total_launches++;
         CREATE_CUDA(cudaMemcpyAsync(ix->h_df.data(), ix->d_df, n_terms * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
+        u64 *d_slot_len = nullptr, *d_slot_dir = nullptr;
+        if (dir_words) {
+            CREATE_CUDA(cudaMalloc(&ix->d_tile_dir, dir_words * sizeof(u32)));
+            ix->device_bytes += dir_words * sizeof(u32);
+            CREATE_CUDA(cudaMalloc(&d_slot_len, n_slots * sizeof(u64)));
+            CREATE_CUDA(cudaMalloc(&d_slot_dir, n_slots * sizeof(u64)));
+            CREATE_CUDA(cudaMemcpyAsync(d_slot_len, slot_len.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+            CREATE_CUDA(cudaMemcpyAsync(d_slot_dir, slot_dir.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+            tile_dir_kernel<<<blocks, 256, 0, ix->stream>>>(ix->d_words, n_words, d_off, d_slot_len, d_slot_dir, n_slots,
+                                                           ix->d_tile_dir, doc_base, n_tiles);
+            CREATE_CUDA(cudaGetLastError());
+            ix->stats.total_launches++;
+        }
         CREATE_CUDA(cudaStreamSynchronize(ix->stream));
         cudaFree(d_off);
         cudaFree(d_slot);
+        cudaFree(d_slot_len);
+        cudaFree(d_slot_dir);
     } else {
         CREATE_CUDA(cudaStreamSynchronize(ix->stream));
     }
@@ -176,6 +235,8 @@ extern "C" int sa_index_destroy(sa_index *ix) {
     cudaFree(ix->d_words);
     cudaFree(ix->d_doc_lens);
     cudaFree(ix->d_df);
+    cudaFree(ix->d_tile_dir);
+    cudaFree(ix->d_norm);
     cudaFree(ix->d_rows);
     cudaFree(ix->d_row_mask);
     ix->dense.release();
@@ -274,8 +335,10 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
     rc = ix->queries.reserve(sizeof(TermQuery));
     if (rc) return rc;
     TermQuery tq;
+    memset(&tq, 0, sizeof(tq));
     tq.word_off = term_id == SA_NO_TERM ? 0 : ix->h_off[term_id];
     tq.n_words = term_id == SA_NO_TERM ? 0 : ix->h_len[term_id];
+    tq.dir_off = term_id == SA_NO_TERM ? SA_NO_DIR : ix->h_dir_off[term_id];
     tq.idf = p.idf;
     SA_CUDA(cudaMemcpyAsync(ix->queries.p, &tq, sizeof(tq), cudaMemcpyHostToDevice, ix->stream));
     TermBatchArgs a;
@@ -334,8 +397,10 @@ struct BatchState {
 
 static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     TermQuery tq;
+    memset(&tq, 0, sizeof(tq));
     tq.word_off = t == SA_NO_TERM ? 0 : ix->h_off[t];
     tq.n_words = t == SA_NO_TERM ? 0 : ix->h_len[t];
+    tq.dir_off = t == SA_NO_TERM ? SA_NO_DIR : ix->h_dir_off[t];
     tq.idf = idf;
     return tq;
 }

@@ -1,20 +1,31 @@
-// sa_term.cu -- the term-at-a-time BM25 scan (the headline kernel).
+// sa_term.cu -- the term-at-a-time BM25 scan (the headline kernel), v2.
 //
 // Replaces, fused into one launch per query batch:
 //   popcount64_reduce   searcharray/roaringish/popcount.pyx:212-237  (tf by doc)
 //   as_dense/scatter    searcharray/roaringish/roaringish_ops.pyx:84-98, scatter_assign.h:8-29
 //   bm25_score          searcharray/bm25/bm25.pyx:11-41
 //
-// Design (B200): the dense float32[N] score vector is cut into tiles of SA_TILE_DOCS docs.
-// One CTA owns one (tile, query): it finds the slice of the term's posting words whose doc
-// ids fall in the tile (warp-cooperative 32-ary search; words are sorted by doc id), streams
-// that slice with coalesced 8-byte loads, accumulates popcounts per doc with shared-memory
-// atomics into a 16 KB tile, then converts the tile to BM25 scores (gathering doc_lens only
-// where tf > 0 -- the hardware fetches only the touched 32 B sectors) and writes it out
-// once, with 16-byte coalesced stores.  HBM traffic = 8*W (words) + <=4*df.. (doc_lens
-// sectors) + 4*N (scores), i.e. the algorithmic minimum of SURVEY.md section 8d.
-// The epilogue optionally feeds the top-k collector (sa_topk.cu) from registers so the
-// dense vector is never re-read.
+// Design (B200).  The dense float32[N] score vector is cut into tiles of SA_TILE_DOCS docs; one
+// CTA owns one (tile, query) and builds the tile in 16 KB of shared memory:
+//   1. the slice [lo,hi) of the term's posting words whose docs fall in the tile comes from the
+//      term's tile directory (two loads; built at upload for long lists) or, for short lists,
+//      from a warp-cooperative 32-ary search;
+//   2. the slice is streamed with coalesced 8-byte loads, one word per thread.  Words are sorted
+//      by doc, so the words of one doc are adjacent: the thread holding the FIRST word of a doc
+//      ("head") adds the popcounts of the doc's run (neighbour via warp shuffle, longer runs by
+//      look-ahead loads), gathers the doc's precomputed BM25 length norm, evaluates
+//      tf/(tf+norm)*idf with individually rounded operations (bit-identical to the reference's
+//      x86-64 build) and stores the score into the shared tile.  No atomics, no work for docs
+//      that do not contain the term;
+//   3. the tile is flushed once with 16-byte streaming stores; while it passes through registers
+//      every score >= a running, provably valid lower bound of the k-th best score is appended to
+//      the query's top-k candidate list (sa_topk.cu), so the dense vector is never re-read.
+// HBM traffic = 8*W (words) + <= 32 B sectors holding the 4*df norms + 4*N (scores): the
+// algorithmic minimum of SURVEY.md section 8d.  v1 of this kernel (profiles/r1a_*) evaluated
+// BM25 for all 16 docs of every thread under divergence and was instruction-bound (47 % issue
+// utilisation at 21 % of the HBM roofline); v2 does work proportional to the postings.
+#include <algorithm>
+
 #include "sa_term.cuh"
 
 __device__ __forceinline__ bool payload_keep(u64 w, u64 lo, u64 hi) {
@@ -33,171 +44,222 @@ __device__ __forceinline__ u32 warp_sort_desc(u32 v) {
             u32 o = __shfl_xor_sync(0xffffffffu, v, j);
             bool up = ((lane & k) == 0);          // descending block
             bool lower = ((lane & j) == 0);
-            u32 mx = v > o ? v : o, mn = v > o ? o : v;
+            u32 mx = max(v, o), mn = min(v, o);
             v = (up == lower) ? mx : mn;
         }
     }
     return v;
 }
 
-template <int MODE, bool ALL_DOCS>
-__global__ void __launch_bounds__(SA_TERM_THREADS)
+__device__ __forceinline__ float bm25_from_norm(float tf, float norm, float idf) {
+    return __fmul_rn(__fdiv_rn(tf, __fadd_rn(tf, norm)), idf);
+}
+
+__device__ __forceinline__ void append_one(u32 *count, u64 *cand, u32 cap, float v, float thr_f, u32 doc) {
+    if (v >= thr_f) {
+        u32 slot = atomicAdd(count, 1u);
+        if (slot < cap) cand[slot] = ((u64)__float_as_uint(v) << 32) | (u64)(0xFFFFFFFFu - doc);
+    }
+}
+
+__device__ __noinline__ void append_candidates(u32 *count, u64 *cand, u32 cap, float4 v, float thr_f, u32 doc0) {
+    append_one(count, cand, cap, v.x, thr_f, doc0);
+    append_one(count, cand, cap, v.y, thr_f, doc0 + 1);
+    append_one(count, cand, cap, v.z, thr_f, doc0 + 2);
+    append_one(count, cand, cap, v.w, thr_f, doc0 + 3);
+}
+
+template <int MODE, bool ALL_DOCS, bool FILTER>
+__global__ void __launch_bounds__(SA_TERM_THREADS, 6)
 term_tile_kernel(const TermBatchArgs a) {
-    __shared__ u32 s_cnt[SA_TILE_DOCS];
-    __shared__ u64 s_range[2];
+    __shared__ __align__(16) float s_out[SA_TILE_DOCS];
+    __shared__ u32 s_range[2];
     __shared__ u32 s_warp_bound[SA_TERM_THREADS / 32];
 
     const u32 q = blockIdx.y;
-    const u64 tile = blockIdx.x;
+    const u32 tile = blockIdx.x;
     const TermQuery tq = a.queries[q];
-    const u64 tile_doc0 = tile * SA_TILE_DOCS;                // local doc index of the tile start
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 *__restrict__ words = a.words + tq.word_off;
+    const u32 n_words = (u32)tq.n_words;
+    const u32 tile_doc0 = tile * SA_TILE_DOCS;                       // local doc index
+    const u32 tile_doc0_abs = (u32)a.doc_base + tile_doc0;           // as stored in the words
 
-    // 1. zero the tile, and (warps 0/1) find the posting slice [lo, hi) of this tile
+    // 1. zero the tile; posting slice [lo, hi) of this tile
 #pragma unroll
     for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
-        reinterpret_cast<uint4 *>(s_cnt)[tid + i * SA_TERM_THREADS] = make_uint4(0, 0, 0, 0);
-    if (warp < 2) {
-        u64 key = a.doc_base + tile_doc0 + (warp ? SA_TILE_DOCS : 0);
-        u64 r = warp_lower_bound_shifted(words, 0, tq.n_words, key, SA_KEY_SHIFT);
-        if (lane == 0) s_range[warp] = r;
-    }
-    __syncthreads();
-    const u64 lo = s_range[0], hi = s_range[1];
-
-    // 2. stream the slice: tf[doc] += popcount(payload)
-    {
-        const u64 base_doc = a.doc_base + tile_doc0;
-        u64 i = lo + tid;
-        // 4 independent loads in flight per thread
-        for (; i + 3 * SA_TERM_THREADS < hi; i += 4 * SA_TERM_THREADS) {
-            u64 w0 = ld_stream_u64(words + i);
-            u64 w1 = ld_stream_u64(words + i + SA_TERM_THREADS);
-            u64 w2 = ld_stream_u64(words + i + 2 * SA_TERM_THREADS);
-            u64 w3 = ld_stream_u64(words + i + 3 * SA_TERM_THREADS);
-            u64 ws[4] = {w0, w1, w2, w3};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                u64 w = ws[j];
-                if (a.filter && !payload_keep(w, a.min_payload, a.max_payload)) continue;
-                u64 d = (w >> SA_KEY_SHIFT) - base_doc;
-                if (d < SA_TILE_DOCS) atomicAdd(&s_cnt[d], (u32)__popcll(w & SA_LSB_MASK));
-            }
+        reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    u32 lo, hi;
+    if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
+        const u32 *dir = a.tile_dir + tq.dir_off + tile;
+        lo = __ldg(dir);
+        hi = __ldg(dir + 1);
+        __syncthreads();
+    } else {
+        if (warp < 2) {
+            u64 key = (u64)tile_doc0_abs + (warp ? SA_TILE_DOCS : 0);
+            u64 r = warp_lower_bound_shifted(words, 0, n_words, key, SA_KEY_SHIFT);
+            if (lane == 0) s_range[warp] = (u32)r;
         }
-        for (; i < hi; i += SA_TERM_THREADS) {
-            u64 w = ld_stream_u64(words + i);
-            if (a.filter && !payload_keep(w, a.min_payload, a.max_payload)) continue;
-            u64 d = (w >> SA_KEY_SHIFT) - base_doc;
-            if (d < SA_TILE_DOCS) atomicAdd(&s_cnt[d], (u32)__popcll(w & SA_LSB_MASK));
-        }
+        __syncthreads();
+        lo = s_range[0];
+        hi = s_range[1];
     }
-    __syncthreads();
 
-    // 3. epilogue: tf -> score, one coalesced 16 B store per 4 docs
-    Bm25Params p = a.bm25;
-    p.idf = tq.idf;
-    float *__restrict__ out = a.out + (u64)q * a.out_stride + tile_doc0;
-    const float *__restrict__ dls = a.doc_lens + tile_doc0;
-    const u64 docs_left = a.n_docs > tile_doc0 ? a.n_docs - tile_doc0 : 0;   // valid docs in tile
-
-    float sc[4][4];
+    // 2. stream the slice, one word per thread; heads score their doc
     u32 my_max = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const unsigned g = tid + j * SA_TERM_THREADS;       // float4 group within the tile
-        uint4 c = reinterpret_cast<const uint4 *>(s_cnt)[g];
-        u32 cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const u64 d = (u64)g * 4 + e;
-            float v;
-            if (MODE == TERM_MODE_TF) {
-                v = (float)cc[e];
-            } else if (ALL_DOCS) {
-                v = (d < docs_left) ? bm25_one((float)cc[e], dls[d], p) : 0.0f;
+    const float *__restrict__ norm = a.norm + tile_doc0;
+    for (u32 base = lo; base < hi; base += SA_TERM_THREADS) {        // CTA-uniform trip count
+        const u32 i = base + tid;
+        const bool act = i < hi;
+        u64 w = act ? __ldg(words + i) : 0ull;
+        u32 rel = act ? ((u32)(w >> SA_KEY_SHIFT) - tile_doc0_abs) : 0xFFFFu;   // < 4096 when valid
+        u32 pc = __popcll(w & SA_LSB_MASK);
+        if (FILTER && !payload_keep(w, a.min_payload, a.max_payload)) pc = 0;
+        const u32 packed = (rel << 8) | pc;                           // doc-in-tile, popcount
+        u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
+        u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
+        bool head;
+        if (lane == 0) head = act && (i == lo || (u32)(__ldg(words + i - 1) >> SA_KEY_SHIFT) - tile_doc0_abs != rel);
+        else head = act && ((prev >> 8) != rel);
+        if (head) {
+            u32 tf = pc;
+            u32 j = i + 1;
+            bool more = false;
+            if (lane != 31) {
+                if ((next >> 8) == rel) { tf += next & 0xFFu; j = i + 2; more = true; }
             } else {
-                v = 0.0f;
-                if (cc[e] != 0 && d < docs_left) v = bm25_one((float)cc[e], __ldg(dls + d), p);
+                more = true;                                          // neighbour is in another warp
             }
-            sc[j][e] = v;
-            if (d < docs_left) {
-                u32 bits = __float_as_uint(v);
-                // only positive finite-or-inf scores are top-k candidates (NaN/negative ignored)
-                if (v > 0.0f && bits > my_max) my_max = bits;
+            if (more) {                                               // runs of >= 3 words / warp edge
+                while (j < n_words) {
+                    u64 w2 = __ldg(words + j);
+                    if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
+                    u32 p2 = __popcll(w2 & SA_LSB_MASK);
+                    if (FILTER && !payload_keep(w2, a.min_payload, a.max_payload)) p2 = 0;
+                    tf += p2;
+                    j++;
+                }
+            }
+            if (rel < SA_TILE_DOCS) {
+                float v;
+                if (MODE == TERM_MODE_TF || ALL_DOCS) {
+                    v = (float)tf;
+                } else {
+                    v = 0.0f;
+                    if (tf) {
+                        v = bm25_from_norm((float)tf, __ldg(norm + rel), tq.idf);
+                        my_max = max(my_max, __float_as_uint(v));
+                    }
+                }
+                s_out[rel] = v;
             }
         }
-        // padded buffer: the whole tile is always in bounds
-        __stcs(reinterpret_cast<float4 *>(out) + g, make_float4(sc[j][0], sc[j][1], sc[j][2], sc[j][3]));
     }
 
-    // 4. optional: feed the top-k collector from registers
-    if (a.topk.k == 0) return;
+    // 3. a valid lower bound on the k-th best score of the whole query: the k-th largest of a
+    //    warp's 32 thread maxima (32 distinct docs); 0 when fewer than k lanes scored anything.
     const u32 k = a.topk.k;
-    // a valid lower bound on the k-th best score: the k-th largest of 32 lane maxima
-    // (32 distinct docs).  0 when the warp holds fewer than k positive lanes.
-    u32 sorted = warp_sort_desc(my_max);
-    u32 wb = __shfl_sync(0xffffffffu, sorted, (k - 1) & 31);
-    if (k > 32) wb = 0;
-    if (lane == 0) s_warp_bound[warp] = wb;
+    if (k) {
+        u32 sorted = warp_sort_desc(my_max);
+        u32 wb = __shfl_sync(0xffffffffu, sorted, (k - 1) & 31);
+        if (lane == 0) s_warp_bound[warp] = (k <= 32) ? wb : 0u;
+    }
     __syncthreads();
-    u32 cta_bound = 0;
+    float thr_f = 0.0f;
+    if (k) {
+        u32 cta_bound = 0;
 #pragma unroll
-    for (int w = 0; w < SA_TERM_THREADS / 32; w++) cta_bound = max(cta_bound, s_warp_bound[w]);
-    u32 thr = *((volatile u32 *)(a.topk.thr_bits + q));
-    if (cta_bound > thr) {
-        if (tid == 0) atomicMax(a.topk.thr_bits + q, cta_bound);
-        thr = cta_bound;
-    }
-    // count my passing values, warp-aggregate one atomicAdd
-    u32 npass = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const u64 d = (u64)(tid + j * SA_TERM_THREADS) * 4 + e;
-            u32 bits = __float_as_uint(sc[j][e]);
-            if (sc[j][e] > 0.0f && bits >= thr && d < docs_left) npass++;
+        for (int wI = 0; wI < SA_TERM_THREADS / 32; wI++) cta_bound = max(cta_bound, s_warp_bound[wI]);
+        u32 thr = __ldcg(a.topk.thr_bits + q);
+        if (cta_bound > thr) {
+            if (tid == 0) atomicMax(a.topk.thr_bits + q, cta_bound);
+            thr = cta_bound;
         }
-    unsigned any = __ballot_sync(0xffffffffu, npass != 0);
-    if (any == 0) return;
-    u32 incl = npass;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        thr = max(thr, 1u);                   // scores are >= +0: bit order == float order; skip zeros
+        thr_f = __uint_as_float(thr);
     }
-    u32 total = __shfl_sync(0xffffffffu, incl, 31);
-    u32 base = 0;
-    if (lane == 0) base = atomicAdd(a.topk.count + q, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    u32 slot = base + incl - npass;
-    u64 *cand = a.topk.cand + (u64)q * a.topk.cap;
+
+    // 4. flush the tile: 16-byte streaming stores (the padded buffer makes the tile always in bounds)
+    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const u64 d = (u64)(tid + j * SA_TERM_THREADS) * 4 + e;
-            u32 bits = __float_as_uint(sc[j][e]);
-            if (sc[j][e] > 0.0f && bits >= thr && d < docs_left) {
-                if (slot < a.topk.cap)
-                    cand[slot] = ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (u32)(tile_doc0 + d));
-                slot++;
-            }
+    for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
+        const unsigned g = tid + jj * SA_TERM_THREADS;
+        float4 v = reinterpret_cast<const float4 *>(s_out)[g];
+        if (ALL_DOCS && MODE == TERM_MODE_SCORE) {
+            // bm25.pyx:20-25 over EVERY doc (NaN / inf / -0.0 cases of exotic parameters)
+            Bm25Params p = a.bm25;
+            p.idf = tq.idf;
+            const u64 d = (u64)tile_doc0 + (u64)g * 4;
+            const float *dl = a.doc_lens + d;
+            v.x = (d + 0 < a.n_docs) ? bm25_one(v.x, dl[0], p) : 0.0f;
+            v.y = (d + 1 < a.n_docs) ? bm25_one(v.y, dl[1], p) : 0.0f;
+            v.z = (d + 2 < a.n_docs) ? bm25_one(v.z, dl[2], p) : 0.0f;
+            v.w = (d + 3 < a.n_docs) ? bm25_one(v.w, dl[3], p) : 0.0f;
         }
+        __stcs(out4 + g, v);
+        if (k) {
+            // NaN compares false; negatives are below thr_f > 0
+            if ((v.x >= thr_f) | (v.y >= thr_f) | (v.z >= thr_f) | (v.w >= thr_f))
+                append_candidates(a.topk.count + q, a.topk.cand + (u64)q * a.topk.cap, a.topk.cap, v, thr_f,
+                                  tile_doc0 + g * 4);
+        }
+    }
 }
 
-int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries) {
-    if (n_queries == 0 || a.n_docs == 0) return SA_OK;
+// per-doc BM25 length norm, the inner part of bm25.pyx:21-23 with the same rounding sequence
+__global__ void norm_kernel(const float *__restrict__ dl, float *__restrict__ norm, u64 n, u64 n_pad,
+                            Bm25Params p) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float v = 0.0f;
+    if (i < n) v = __fmul_rn(p.k1, __fadd_rn(p.one_minus_b, __fmul_rn(p.b, __fdiv_rn(dl[i], p.avg_doc_len))));
+    norm[i] = v;
+}
+
+int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len) {
+    if (ix->norm_valid && ix->norm_k1 == k1 && ix->norm_b == b && ix->norm_avgdl == avg_doc_len) return SA_OK;
+    const u64 n_pad = (ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS;
+    if (!ix->d_norm) {
+        SA_CUDA(cudaMalloc(&ix->d_norm, std::max<u64>(n_pad, 1) * sizeof(float)));
+        ix->device_bytes += n_pad * sizeof(float);
+    }
+    Bm25Params p;
+    p.idf = 0; p.avg_doc_len = avg_doc_len; p.k1 = k1; p.b = b; p.one_minus_b = 1 - b; p.sparse_ok = 1;
+    if (n_pad) {
+        norm_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, ix->stream>>>(ix->d_doc_lens, ix->d_norm, ix->n_docs, n_pad, p);
+        SA_CUDA(cudaGetLastError());
+        ix->stats.total_launches++;
+    }
+    ix->norm_k1 = k1; ix->norm_b = b; ix->norm_avgdl = avg_doc_len;
+    ix->norm_valid = true;
+    return SA_OK;
+}
+
+int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
+    if (n_queries == 0 || a_in.n_docs == 0) return SA_OK;
+    TermBatchArgs a = a_in;
+    a.tile_dir = ix->d_tile_dir;
+    a.norm = ix->d_norm;
+    const bool sparse_score = (a.mode == TERM_MODE_SCORE) && a.bm25.sparse_ok;
+    if (sparse_score) {
+        int rc = sa_ensure_norm(ix, a.bm25.k1, a.bm25.b, a.bm25.avg_doc_len);
+        if (rc) return rc;
+        a.norm = ix->d_norm;
+    }
     dim3 grid((unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS), n_queries);
     dim3 block(SA_TERM_THREADS);
     KernelTimer t(ix, 0);
-    if (a.mode == TERM_MODE_TF)
-        term_tile_kernel<TERM_MODE_TF, false><<<grid, block, 0, ix->stream>>>(a);
-    else if (a.bm25.sparse_ok)
-        term_tile_kernel<TERM_MODE_SCORE, false><<<grid, block, 0, ix->stream>>>(a);
-    else
-        term_tile_kernel<TERM_MODE_SCORE, true><<<grid, block, 0, ix->stream>>>(a);
+    if (a.mode == TERM_MODE_TF) {
+        if (a.filter) term_tile_kernel<TERM_MODE_TF, false, true><<<grid, block, 0, ix->stream>>>(a);
+        else term_tile_kernel<TERM_MODE_TF, false, false><<<grid, block, 0, ix->stream>>>(a);
+    } else if (sparse_score) {
+        if (a.filter) term_tile_kernel<TERM_MODE_SCORE, false, true><<<grid, block, 0, ix->stream>>>(a);
+        else term_tile_kernel<TERM_MODE_SCORE, false, false><<<grid, block, 0, ix->stream>>>(a);
+    } else {
+        if (a.filter) term_tile_kernel<TERM_MODE_SCORE, true, true><<<grid, block, 0, ix->stream>>>(a);
+        else term_tile_kernel<TERM_MODE_SCORE, true, false><<<grid, block, 0, ix->stream>>>(a);
+    }
     SA_CUDA(cudaGetLastError());
     t.stop();
     ix->stats.term_kernel_launches++;

@@ -20,6 +20,8 @@ struct TopkCtx {
 struct TermBatchArgs {
     const u64 *words;
     const float *doc_lens;
+    const float *norm;          // per-doc BM25 length norm (padded to a tile multiple), SCORE mode
+    const u32 *tile_dir;        // tile directories (see sa_index::d_tile_dir)
     u64 n_docs;
     u64 doc_base;
     const TermQuery *queries;   // [Q]
@@ -33,6 +35,7 @@ struct TermBatchArgs {
 };
 
 int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries);
+int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len);
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys);
 int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
 // batch plumbing shared by sa_index.cu / sa_comm.cu (callers hold ix->mu)
