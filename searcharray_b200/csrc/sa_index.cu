@@ -386,13 +386,13 @@ extern "C" int sa_score_term(sa_index *ix, uint32_t term_id, float idf, float av
 // ------------------------------------------------ batched, HBM-resident top-k
 // A prepared batch: query descriptors live in HBM; sa_batch_execute only enqueues kernels.
 struct BatchState {
-    u32 nq = 0, k = 0, cap = 0, chunk = 0;
+    u32 nq = 0, k = 0, slots = 0, chunk = 0;
     float avg_doc_len = 0, k1 = 0, b = 0;
     bool ready = false;
     std::vector<TermQuery> qs;
     std::vector<Bm25Params> chunk_params;     // per chunk (sparse_ok must hold for every idf in it)
     DevBuf d_queries;                          // TermQuery[nq]
-    DevBuf d_meta;                             // u32 thr[nq], u32 count[nq]
+    DevBuf d_meta;                             // u32 overflow[nq]
 };
 
 static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
@@ -405,10 +405,14 @@ static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     return tq;
 }
 
-// Enqueue scoring + candidate collection + select for queries [q0, q0+Q) (async).
-static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_thr, u32 *d_count,
-                              u32 Q, const Bm25Params &p, u32 k, u32 cap, u64 *d_keys) {
+static u32 n_tiles_of(const sa_index *ix) { return (u32)((ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS); }
+
+// Enqueue scoring + candidate collection + select for Q queries (async).  ix->cand must hold
+// Q * n_tiles * (slots * 8 + 4) bytes.
+static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_overflow,
+                              u32 Q, const Bm25Params &p, u32 k, u32 slots, u64 *d_keys) {
     const u64 stride = padded_docs(ix->n_docs);
+    const u32 T = n_tiles_of(ix);
     TermBatchArgs a;
     memset(&a, 0, sizeof(a));
     a.words = ix->d_words;
@@ -423,14 +427,19 @@ static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_t
     a.max_payload = SA_ALL_BITS;
     a.filter = 0;
     a.mode = TERM_MODE_SCORE;
-    a.topk.thr_bits = d_thr;
-    a.topk.count = d_count;
-    a.topk.cand = ix->cand.as<u64>();
-    a.topk.cap = cap;
+    a.topk.tile_cand = ix->cand.as<u64>();
+    a.topk.tile_cnt = (u32 *)(a.topk.tile_cand + (u64)Q * T * slots);
+    a.topk.overflow = d_overflow;
+    a.topk.n_tiles = T;
+    a.topk.slots = slots;
     a.topk.k = k;
     int rc;
     if ((rc = launch_term_batch(ix, a, Q))) return rc;
     return launch_topk_select(ix, a.topk, Q, ix->doc_base, d_keys);
+}
+
+static size_t cand_bytes(const sa_index *ix, u32 Q, u32 slots) {
+    return (size_t)Q * n_tiles_of(ix) * ((size_t)slots * sizeof(u64) + sizeof(u32)) + 64;
 }
 
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
@@ -445,6 +454,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     B.ready = false;
     B.nq = n_queries;
     B.k = k;
+    B.slots = sa_topk_slots(k);
     B.avg_doc_len = avg_doc_len;
     B.k1 = k1;
     B.b = b;
@@ -457,7 +467,6 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     // chunk so the dense score vectors of one chunk stay within ~4 GB of HBM
     u32 chunk = (u32)std::max<u64>(1, std::min<u64>(n_queries, (4ull << 30) / (stride * sizeof(float))));
     B.chunk = std::min<u32>(chunk, 65535);
-    B.cap = (u32)std::max<u64>(1, std::min<u64>(ix->n_docs, 1u << 16));
     for (u32 q = 0; q < n_queries; q++) {
         SA_CHECK(term_starts[q + 1] - term_starts[q] == 1,
                  "query %u: phrase queries in a batch are not supported yet", q);
@@ -472,9 +481,9 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
         B.chunk_params.push_back(p);
     }
     if ((rc = ix->dense.reserve((size_t)B.chunk * stride * sizeof(float)))) return rc;
-    if ((rc = ix->cand.reserve((size_t)B.chunk * B.cap * sizeof(u64)))) return rc;
+    if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
     if ((rc = B.d_queries.reserve((size_t)n_queries * sizeof(TermQuery)))) return rc;
-    if ((rc = B.d_meta.reserve((size_t)n_queries * 2 * sizeof(u32)))) return rc;
+    if ((rc = B.d_meta.reserve((size_t)n_queries * sizeof(u32)))) return rc;
     SA_CUDA(cudaMemcpyAsync(B.d_queries.p, B.qs.data(), (size_t)n_queries * sizeof(TermQuery),
                             cudaMemcpyHostToDevice, ix->stream));
     B.ready = true;
@@ -487,47 +496,48 @@ int sa_batch_execute_locked(sa_index *ix) {
     SA_CUDA(cudaSetDevice(ix->device));
     u64 *d_keys = ix->topk_out.as<u64>();
     if (B.nq == 0) return SA_OK;
-    SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)B.nq * B.k * sizeof(u64), ix->stream));
-    if (ix->n_docs == 0 || B.avg_doc_len == 0.0f) return SA_OK;
-    u32 *d_thr = B.d_meta.as<u32>(), *d_count = d_thr + B.nq;
-    SA_CUDA(cudaMemsetAsync(d_thr, 0, (size_t)B.nq * 2 * sizeof(u32), ix->stream));
+    if (ix->n_docs == 0 || B.avg_doc_len == 0.0f) {
+        SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)B.nq * B.k * sizeof(u64), ix->stream));
+        return SA_OK;
+    }
+    u32 *d_ovf = B.d_meta.as<u32>();
+    SA_CUDA(cudaMemsetAsync(d_ovf, 0, (size_t)B.nq * sizeof(u32), ix->stream));
     u32 ci = 0;
     for (u32 q0 = 0; q0 < B.nq; q0 += B.chunk, ci++) {
         const u32 Q = std::min(B.chunk, B.nq - q0);
-        int rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q0, d_thr + q0, d_count + q0, Q,
-                                    B.chunk_params[ci], B.k, B.cap, d_keys + (u64)q0 * B.k);
+        int rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q0, d_ovf + q0, Q,
+                                    B.chunk_params[ci], B.k, B.slots, d_keys + (u64)q0 * B.k);
         if (rc) return rc;
     }
     return SA_OK;
 }
 
-// After execute: re-run (synchronously) the queries whose candidate list overflowed.
+// After execute: re-run (synchronously) the queries whose per-tile candidate slots overflowed.
 int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
     BatchState &B = *ix->batch;
     if (n_redone) *n_redone = 0;
     if (B.nq == 0 || ix->n_docs == 0 || B.avg_doc_len == 0.0f) return SA_OK;
     int rc;
     if ((rc = sa_pinned_reserve(ix, std::max<size_t>((size_t)B.nq * sizeof(u32), 4096)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, B.d_meta.as<u32>() + B.nq, (size_t)B.nq * sizeof(u32),
-                            cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, B.d_meta.p, (size_t)B.nq * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
     std::vector<u32> redo;
-    const u32 *counts = (const u32 *)ix->h_pinned;
-    for (u32 q = 0; q < B.nq; q++) if (counts[q] > B.cap) redo.push_back(q);
+    const u32 *ovf = (const u32 *)ix->h_pinned;
+    for (u32 q = 0; q < B.nq; q++) if (ovf[q]) redo.push_back(q);
     if (redo.empty()) return SA_OK;
-    // candidate overflow (threshold rose too slowly, e.g. scores ascending with doc id, or
-    // massive ties): one query at a time with room for every doc.
-    if ((rc = ix->cand.reserve((size_t)ix->n_docs * sizeof(u64)))) return rc;
-    u32 *d_thr = B.d_meta.as<u32>(), *d_count = d_thr + B.nq;
+    // a tile had more candidates than slots (massive ties / adversarial score layout): one
+    // query at a time with a slot for every doc of the tile -- cannot overflow, stays exact.
+    if ((rc = ix->cand.reserve(cand_bytes(ix, 1, SA_TILE_DOCS)))) return rc;
     for (u32 q : redo) {
-        SA_CUDA(cudaMemsetAsync(d_thr + q, 0, sizeof(u32), ix->stream));
-        SA_CUDA(cudaMemsetAsync(d_count + q, 0, sizeof(u32), ix->stream));
+        SA_CUDA(cudaMemsetAsync(B.d_meta.as<u32>() + q, 0, sizeof(u32), ix->stream));
         Bm25Params p = make_bm25(ix, B.qs[q].idf, B.avg_doc_len, B.k1, B.b);
-        rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q, d_thr + q, d_count + q, 1, p, B.k,
-                                (u32)ix->n_docs, ix->topk_out.as<u64>() + (u64)q * B.k);
+        rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q, B.d_meta.as<u32>() + q, 1, p, B.k,
+                                SA_TILE_DOCS, ix->topk_out.as<u64>() + (u64)q * B.k);
         if (rc) return rc;
     }
     SA_CUDA(cudaStreamSynchronize(ix->stream));
+    // the big buffer is only for repairs: give the batch its normal one back
+    if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
     if (n_redone) *n_redone = (u32)redo.size();
     return SA_OK;
 }

@@ -55,18 +55,23 @@ __device__ __forceinline__ float bm25_from_norm(float tf, float norm, float idf)
     return __fmul_rn(__fdiv_rn(tf, __fadd_rn(tf, norm)), idf);
 }
 
-__device__ __forceinline__ void append_one(u32 *count, u64 *cand, u32 cap, float v, float thr_f, u32 doc) {
-    if (v >= thr_f) {
-        u32 slot = atomicAdd(count, 1u);
-        if (slot < cap) cand[slot] = ((u64)__float_as_uint(v) << 32) | (u64)(0xFFFFFFFFu - doc);
+// k-th largest (k <= 32) of the CTA's thread maxima, computed redundantly by every warp from the
+// per-warp sorted lists in shared memory (top `m` of each of the 8 warps).  Any such value is a
+// valid lower bound of the tile's k-th best score (the maxima belong to distinct docs).
+__device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k) {
+    const unsigned lane = threadIdx.x & 31;
+    if (k <= 10) {
+        // union of each warp's top-4: exact unless one warp holds > 4 of the CTA's top-k
+        u32 v = s_top[(lane >> 2) * 8 + (lane & 3)];
+        v = warp_sort_desc(v);
+        return __shfl_sync(0xffffffffu, v, k - 1);
     }
-}
-
-__device__ __noinline__ void append_candidates(u32 *count, u64 *cand, u32 cap, float4 v, float thr_f, u32 doc0) {
-    append_one(count, cand, cap, v.x, thr_f, doc0);
-    append_one(count, cand, cap, v.y, thr_f, doc0 + 1);
-    append_one(count, cand, cap, v.z, thr_f, doc0 + 2);
-    append_one(count, cand, cap, v.w, thr_f, doc0 + 3);
+    // union of each warp's top-8 (64 values): two sorted runs of 32, top-32 by the bitonic max trick
+    u32 a = warp_sort_desc(s_top[(lane >> 3) * 8 + (lane & 7)]);
+    u32 b = warp_sort_desc(s_top[32 + (lane >> 3) * 8 + (lane & 7)]);
+    u32 c = max(a, __shfl_sync(0xffffffffu, b, 31 - lane));      // the 32 largest of the 64
+    c = warp_sort_desc(c);
+    return __shfl_sync(0xffffffffu, c, k - 1);
 }
 
 template <int MODE, bool ALL_DOCS, bool FILTER>
@@ -74,7 +79,8 @@ __global__ void __launch_bounds__(SA_TERM_THREADS, 6)
 term_tile_kernel(const TermBatchArgs a) {
     __shared__ __align__(16) float s_out[SA_TILE_DOCS];
     __shared__ u32 s_range[2];
-    __shared__ u32 s_warp_bound[SA_TERM_THREADS / 32];
+    __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
+    __shared__ u32 s_ncand;
 
     const u32 q = blockIdx.y;
     const u32 tile = blockIdx.x;
@@ -157,28 +163,22 @@ term_tile_kernel(const TermBatchArgs a) {
         }
     }
 
-    // 3. a valid lower bound on the k-th best score of the whole query: the k-th largest of a
-    //    warp's 32 thread maxima (32 distinct docs); 0 when fewer than k lanes scored anything.
+    // 3. top-k: each warp publishes its 8 largest thread maxima (sorted) ...
     const u32 k = a.topk.k;
     if (k) {
         u32 sorted = warp_sort_desc(my_max);
-        u32 wb = __shfl_sync(0xffffffffu, sorted, (k - 1) & 31);
-        if (lane == 0) s_warp_bound[warp] = (k <= 32) ? wb : 0u;
+        if (lane < 8) s_top[warp * 8 + lane] = sorted;
+        if (tid == 0) s_ncand = 0;
     }
     __syncthreads();
+    // ... and every warp derives the same tile bound; scores >= bound are this tile's candidates
     float thr_f = 0.0f;
     if (k) {
-        u32 cta_bound = 0;
-#pragma unroll
-        for (int wI = 0; wI < SA_TERM_THREADS / 32; wI++) cta_bound = max(cta_bound, s_warp_bound[wI]);
-        u32 thr = __ldcg(a.topk.thr_bits + q);
-        if (cta_bound > thr) {
-            if (tid == 0) atomicMax(a.topk.thr_bits + q, cta_bound);
-            thr = cta_bound;
-        }
-        thr = max(thr, 1u);                   // scores are >= +0: bit order == float order; skip zeros
+        u32 thr = max(cta_kth_bound(s_top, k), 1u);   // >= 1: skip zeros (scores are >= +0.0)
         thr_f = __uint_as_float(thr);
     }
+    u64 *__restrict__ my_cand = nullptr;
+    if (k) my_cand = a.topk.tile_cand + ((u64)q * a.topk.n_tiles + tile) * a.topk.slots;
 
     // 4. flush the tile: 16-byte streaming stores (the padded buffer makes the tile always in bounds)
     float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
@@ -200,9 +200,26 @@ term_tile_kernel(const TermBatchArgs a) {
         __stcs(out4 + g, v);
         if (k) {
             // NaN compares false; negatives are below thr_f > 0
-            if ((v.x >= thr_f) | (v.y >= thr_f) | (v.z >= thr_f) | (v.w >= thr_f))
-                append_candidates(a.topk.count + q, a.topk.cand + (u64)q * a.topk.cap, a.topk.cap, v, thr_f,
-                                  tile_doc0 + g * 4);
+            if ((v.x >= thr_f) | (v.y >= thr_f) | (v.z >= thr_f) | (v.w >= thr_f)) {
+                const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (vs[e] >= thr_f) {
+                        u32 slot = atomicAdd(&s_ncand, 1u);           // shared-memory atomic
+                        if (slot < a.topk.slots)
+                            my_cand[slot] = ((u64)__float_as_uint(vs[e]) << 32) |
+                                            (u64)(0xFFFFFFFFu - (tile_doc0 + g * 4 + e));
+                    }
+                }
+            }
+        }
+    }
+    if (k) {
+        __syncthreads();
+        if (tid == 0) {
+            u32 n = s_ncand;
+            a.topk.tile_cnt[(u64)q * a.topk.n_tiles + tile] = min(n, a.topk.slots);
+            if (n > a.topk.slots) a.topk.overflow[q] = 1u;
         }
     }
 }

@@ -8,12 +8,14 @@
 
 enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
 
-// Per-query top-k collection state in HBM (see sa_topk.cu).
+// Per-query top-k collection state in HBM (see sa_topk.cu).  No global atomics: every
+// (query, tile) CTA owns `slots` candidate slots.
 struct TopkCtx {
-    u32 *thr_bits;     // [Q] running lower bound on the k-th best score (float bits; scores >= 0)
-    u32 *count;        // [Q] candidates appended (may exceed cap -> overflow)
-    u64 *cand;         // [Q][cap] key = score_bits << 32 | (0xFFFFFFFF - local_doc)
-    u32 cap;
+    u32 *tile_cnt;     // [Q][n_tiles] candidates written by the tile's CTA (<= slots)
+    u64 *tile_cand;    // [Q][n_tiles][slots] key = score_bits << 32 | (0xFFFFFFFF - local_doc)
+    u32 *overflow;     // [Q] set when some tile had more than `slots` candidates
+    u32 n_tiles;
+    u32 slots;
     u32 k;             // 0 => no top-k collection
 };
 
@@ -37,6 +39,7 @@ struct TermBatchArgs {
 int launch_term_batch(sa_index *ix, const TermBatchArgs &a, u32 n_queries);
 int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len);
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys);
+u32 sa_topk_slots(u32 k);
 int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
 // batch plumbing shared by sa_index.cu / sa_comm.cu (callers hold ix->mu)
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,

@@ -4,9 +4,9 @@
 // for the HBM-resident batched path.  The scoring kernels append every score that is >= a
 // running, provably-valid lower bound of the k-th best score (sa_term.cu step 4), so the
 // candidate list is a superset of the true top-k and is normally a few hundred entries.
-// Here one CTA per query selects the exact k best by (score desc, doc id asc):
-// candidates <= 4096 -> bitonic sort in shared memory; more -> 8-bit MSB radix select to the
-// k-th key, then sort the survivors.
+// Here one CTA per query selects the exact k best by (score desc, doc id asc): a tight threshold
+// (k-th largest of the per-tile maxima) prefilters the per-tile candidate slots to ~k survivors,
+// which are sorted in shared memory (bitonic); a radix select handles massive ties.
 #include "sa_term.cuh"
 
 #define SEL_THREADS 512
@@ -28,6 +28,18 @@ __device__ void bitonic_sort_desc_smem(u64 *s, u32 n_pow2) {
     }
 }
 
+// visit every candidate key of query q (tiles strided over threads)
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const TopkCtx &t, u32 q, F f) {
+    const u32 *cnt = t.tile_cnt + (u64)q * t.n_tiles;
+    const u64 *cand = t.tile_cand + (u64)q * t.n_tiles * t.slots;
+    for (u32 tile = threadIdx.x; tile < t.n_tiles; tile += blockDim.x) {
+        const u32 n = cnt[tile];
+        const u64 *c = cand + (u64)tile * t.slots;
+        for (u32 j = 0; j < n; j++) f(c[j]);
+    }
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
     __shared__ u64 s_keys[SEL_SMEM_KEYS];
@@ -37,32 +49,65 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
 
     const u32 q = blockIdx.x;
     const u32 k = t.k;
-    u32 M = t.count[q];
-    if (M > t.cap) M = t.cap;             // overflow: the host re-runs this query
-    const u64 *__restrict__ keys = t.cand + (u64)q * t.cap;
-    u32 n_valid;                           // number of keys in s_keys
+    const u32 T = t.n_tiles;
 
+    // A. a tight valid threshold: the k-th largest of the per-tile-group maxima (distinct docs)
+    const u32 gs = (T + SEL_SMEM_KEYS - 1) / SEL_SMEM_KEYS;          // tiles per group
+    const u32 G = (T + gs - 1) / gs;
+    {
+        const u32 *cnt = t.tile_cnt + (u64)q * T;
+        const u64 *cand = t.tile_cand + (u64)q * T * t.slots;
+        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+            u64 m = 0;
+            for (u32 tile = g * gs; tile < min(T, (g + 1) * gs); tile++) {
+                const u32 n = cnt[tile];
+                const u64 *c = cand + (u64)tile * t.slots;
+                for (u32 j = 0; j < n; j++) m = max(m, c[j]);
+            }
+            s_keys[g] = m;
+        }
+    }
+    u32 g2 = 2;
+    while (g2 < G) g2 <<= 1;
+    for (u32 i = G + threadIdx.x; i < g2; i += blockDim.x) s_keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc_smem(s_keys, g2);
+    u64 thr = (k - 1 < g2) ? s_keys[k - 1] : 0ull;     // 0 => fewer than k groups have a candidate
+    if (thr == 0ull) thr = 1ull;
+    __syncthreads();
+
+    // B. survivors >= thr (a superset of the true top-k, normally ~k of them)
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for_each_candidate(t, q, [&](u64 key) {
+        if (key >= thr) {
+            u32 slot = atomicAdd(&s_n, 1u);
+            if (slot < SEL_SMEM_KEYS) s_keys[slot] = key;
+        }
+    });
+    __syncthreads();
+    u32 M = s_n;
+    u32 n_valid;
     if (M <= SEL_SMEM_KEYS) {
-        u32 n2 = 1;
+        u32 n2 = 2;
         while (n2 < M) n2 <<= 1;
-        if (n2 < 2) n2 = 2;
-        for (u32 i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < M ? keys[i] : 0ull;
+        for (u32 i = M + threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = 0ull;
         __syncthreads();
         bitonic_sort_desc_smem(s_keys, n2);
         n_valid = M;
     } else {
-        // radix select: find the k-th largest key (keys are unique: the doc id is in them)
+        // massive ties around the threshold: radix-select the exact k-th key over all survivors
         if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
         __syncthreads();
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
             __syncthreads();
             const u64 prefix = s_prefix;
-            for (u32 i = threadIdx.x; i < M; i += blockDim.x) {
-                u64 key = keys[i];
+            for_each_candidate(t, q, [&](u64 key) {
+                if (key < thr) return;
                 bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
                 if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
-            }
+            });
             __syncthreads();
             if (threadIdx.x == 0) {
                 u32 rem = s_krem, acc = 0;
@@ -76,16 +121,15 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
             }
             __syncthreads();
         }
-        const u64 kth = s_prefix;          // exact k-th largest key (M > 4096 >= k)
+        const u64 kth = s_prefix;
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        for (u32 i = threadIdx.x; i < M; i += blockDim.x) {
-            u64 key = keys[i];
+        for_each_candidate(t, q, [&](u64 key) {
             if (key >= kth) {
                 u32 slot = atomicAdd(&s_n, 1u);
                 if (slot < SEL_SMEM_KEYS) s_keys[slot] = key;
             }
-        }
+        });
         __syncthreads();
         n_valid = min(s_n, (u32)SEL_SMEM_KEYS);
         u32 n2 = 2;
@@ -146,3 +190,5 @@ int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u
     ix->stats.total_launches++;
     return SA_OK;
 }
+
+u32 sa_topk_slots(u32 k) { return k <= 16 ? 64u : 128u; }
