@@ -34,44 +34,40 @@ __device__ __forceinline__ bool payload_keep(u64 w, u64 lo, u64 hi) {
     return v >= lo && v <= hi;
 }
 
-// Sort 32 values (one per lane) descending across the warp (bitonic network).
-__device__ __forceinline__ u32 warp_sort_desc(u32 v) {
-    const unsigned lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            u32 o = __shfl_xor_sync(0xffffffffu, v, j);
-            bool up = ((lane & k) == 0);          // descending block
-            bool lower = ((lane & j) == 0);
-            u32 mx = max(v, o), mn = min(v, o);
-            v = (up == lower) ? mx : mn;
-        }
-    }
-    return v;
-}
-
 __device__ __forceinline__ float bm25_from_norm(float tf, float norm, float idf) {
     return __fmul_rn(__fdiv_rn(tf, __fadd_rn(tf, norm)), idf);
 }
 
-// k-th largest (k <= 32) of the CTA's thread maxima, computed redundantly by every warp from the
-// per-warp sorted lists in shared memory (top `m` of each of the 8 warps).  Any such value is a
-// valid lower bound of the tile's k-th best score (the maxima belong to distinct docs).
+// The j-th round of "take the warp maximum, then clear it" (REDUX.MAX: one instruction per
+// round on sm_80+).  Equal values collapse into one, which can only lower the resulting bound
+// -- it stays a valid lower bound of the k-th best score.
+__device__ __forceinline__ u32 warp_pop_max(u32 &v) {
+    u32 m = __reduce_max_sync(0xffffffffu, v);
+    if (v == m) v = 0;
+    return m;
+}
+
+// k-th largest (k <= 32) of the CTA's thread maxima, from the per-warp top-M lists in shared
+// memory (M = 4 for k <= 10 else 8; exact unless one warp holds more than M of the CTA's top k).
+// Every warp computes it redundantly (~4k instructions... 4 per round), no extra barrier.
 __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k) {
     const unsigned lane = threadIdx.x & 31;
+    u32 v0, v1 = 0;
     if (k <= 10) {
-        // union of each warp's top-4: exact unless one warp holds > 4 of the CTA's top-k
-        u32 v = s_top[(lane >> 2) * 8 + (lane & 3)];
-        v = warp_sort_desc(v);
-        return __shfl_sync(0xffffffffu, v, k - 1);
+        v0 = s_top[(lane >> 2) * 8 + (lane & 3)];
+    } else {
+        v0 = s_top[lane];
+        v1 = s_top[32 + lane];
     }
-    // union of each warp's top-8 (64 values): two sorted runs of 32, top-32 by the bitonic max trick
-    u32 a = warp_sort_desc(s_top[(lane >> 3) * 8 + (lane & 7)]);
-    u32 b = warp_sort_desc(s_top[32 + (lane >> 3) * 8 + (lane & 7)]);
-    u32 c = max(a, __shfl_sync(0xffffffffu, b, 31 - lane));      // the 32 largest of the 64
-    c = warp_sort_desc(c);
-    return __shfl_sync(0xffffffffu, c, k - 1);
+    u32 kth = 0;
+    for (u32 r = 0; r < k; r++) {
+        u32 m0 = __reduce_max_sync(0xffffffffu, max(v0, v1));
+        if (v0 == m0) v0 = 0;
+        else if (v1 == m0) v1 = 0;
+        kth = m0;
+        if (m0 == 0) break;
+    }
+    return kth;
 }
 
 template <int MODE, bool ALL_DOCS, bool FILTER>
@@ -125,19 +121,25 @@ term_tile_kernel(const TermBatchArgs a) {
         const u32 packed = (rel << 8) | pc;                           // doc-in-tile, popcount
         u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
         u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
+        u32 next2 = __shfl_down_sync(0xffffffffu, packed, 2);
         bool head;
         if (lane == 0) head = act && (i == lo || (u32)(__ldg(words + i - 1) >> SA_KEY_SHIFT) - tile_doc0_abs != rel);
         else head = act && ((prev >> 8) != rel);
         if (head) {
             u32 tf = pc;
             u32 j = i + 1;
-            bool more = false;
-            if (lane != 31) {
-                if ((next >> 8) == rel) { tf += next & 0xFFu; j = i + 2; more = true; }
-            } else {
-                more = true;                                          // neighbour is in another warp
+            bool more = (lane == 31);                                 // neighbour is in another warp
+            if (lane < 31 && (next >> 8) == rel) {
+                tf += next & 0xFFu;
+                j = i + 2;
+                more = (lane == 30);
+                if (lane < 30 && (next2 >> 8) == rel) {
+                    tf += next2 & 0xFFu;
+                    j = i + 3;
+                    more = true;                                      // runs of >= 4 words: look ahead
+                }
             }
-            if (more) {                                               // runs of >= 3 words / warp edge
+            if (more) {
                 while (j < n_words) {
                     u64 w2 = __ldg(words + j);
                     if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
@@ -163,18 +165,25 @@ term_tile_kernel(const TermBatchArgs a) {
         }
     }
 
-    // 3. top-k: each warp publishes its 8 largest thread maxima (sorted) ...
+    // 3. top-k.  A tile with no more words than candidate slots needs no bound: every positive
+    //    score fits.  Otherwise each warp publishes its largest thread maxima and every warp
+    //    derives the same tile bound; scores >= bound are this tile's candidates.
     const u32 k = a.topk.k;
-    if (k) {
-        u32 sorted = warp_sort_desc(my_max);
-        if (lane < 8) s_top[warp * 8 + lane] = sorted;
-        if (tid == 0) s_ncand = 0;
+    const bool need_bound = k && (hi - lo) > a.topk.slots;          // CTA-uniform
+    if (need_bound) {
+        const u32 M = (k <= 10) ? 4u : 8u;
+        u32 v = my_max;
+        for (u32 r = 0; r < M; r++) {
+            u32 m = warp_pop_max(v);
+            if (lane == r) s_top[warp * 8 + r] = m;
+        }
     }
+    if (k && tid == 0) s_ncand = 0;
     __syncthreads();
-    // ... and every warp derives the same tile bound; scores >= bound are this tile's candidates
     float thr_f = 0.0f;
     if (k) {
-        u32 thr = max(cta_kth_bound(s_top, k), 1u);   // >= 1: skip zeros (scores are >= +0.0)
+        u32 thr = 1u;                                   // >= 1: skip zeros (scores are >= +0.0)
+        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
         thr_f = __uint_as_float(thr);
     }
     u64 *__restrict__ my_cand = nullptr;
