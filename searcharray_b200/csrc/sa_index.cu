@@ -136,8 +136,8 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
     CREATE_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaEventCreate(&ix->ev0));
     CREATE_CUDA(cudaEventCreate(&ix->ev1));
-    CREATE_CUDA(cudaMalloc(&ix->d_words, (n_words + 1) * sizeof(u64)));
-    CREATE_CUDA(cudaMemsetAsync(ix->d_words + n_words, 0, sizeof(u64), ix->stream));
+    CREATE_CUDA(cudaMalloc(&ix->d_words, (n_words + 4) * sizeof(u64)));
+    CREATE_CUDA(cudaMemsetAsync(ix->d_words + n_words, 0, 4 * sizeof(u64), ix->stream));
     if (n_words)
         CREATE_CUDA(cudaMemcpyAsync(ix->d_words, words, n_words * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
     CREATE_CUDA(cudaMalloc(&ix->d_doc_lens, (n_docs + 1) * sizeof(float)));
