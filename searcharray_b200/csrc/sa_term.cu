@@ -10,21 +10,23 @@
 //   1. the slice [lo,hi) of the term's posting words whose docs fall in the tile comes from the
 //      term's tile directory (two loads; built at upload for long lists) or, for short lists,
 //      from a warp-cooperative 32-ary search;
-//   2. the slice is staged into shared memory by the TMA engine (one elected thread issues
-//      cp.async.bulk, completion on an mbarrier) while the CTA zeroes the score tile.  Words are
-//      sorted by doc, so the words of one doc are adjacent: the thread holding the FIRST word of
-//      a doc ("head") adds the popcounts of the doc's run, all heads gather their doc's
-//      precomputed BM25 length norm (loads issued back to back), then evaluate
-//      tf/(tf+norm)*idf with individually rounded operations (bit-identical to the reference's
-//      x86-64 build) and store the score into the shared tile.  No atomics, no work for docs
-//      that do not contain the term;
+//   2. the slice is streamed with coalesced 8-byte loads (4 windows in flight per thread).  Words
+//      are sorted by doc, so the words of one doc are adjacent: the thread holding the FIRST word
+//      of a doc ("head") adds the popcounts of the doc's run (neighbours via warp shuffle over
+//      overlapping 32-lane windows), gathers the doc's precomputed BM25 length norm (gathers
+//      issued back to back), evaluates tf/(tf+norm)*idf with individually rounded operations
+//      (bit-identical to the reference's x86-64 build) and stores the score into the shared
+//      tile.  No atomics, no work for docs that do not contain the term;
 //   3. the tile is flushed once with 16-byte streaming stores; while it passes through registers
 //      every score >= a running, provably valid lower bound of the k-th best score is appended to
 //      the query's top-k candidate list (sa_topk.cu), so the dense vector is never re-read.
 // HBM traffic = 8*W (words) + <= 32 B sectors holding the 4*df norms + 4*N (scores): the
 // algorithmic minimum of SURVEY.md section 8d.  v1 of this kernel (profiles/r1a_*) evaluated
 // BM25 for all 16 docs of every thread under divergence and was instruction-bound (47 % issue
-// utilisation at 21 % of the HBM roofline); v2 does work proportional to the postings.
+// utilisation at 21 % of the HBM roofline); v2 does work proportional to the postings.  A variant
+// staging the slice with TMA bulk copies (cp.async.bulk + mbarrier) was measured slower on every
+// df bucket (profiles/README.md): the scan is bound by instruction issue on dense terms and by the
+// dense 4N write otherwise, not by load latency.
 #include <algorithm>
 
 #include "sa_term.cuh"
@@ -71,42 +73,10 @@ __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k)
     return kth;
 }
 
-// ---- TMA 1-D bulk copy (cp.async.bulk) + mbarrier, single CTA --------------------------------
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); the
-// mbarrier receives the transaction bytes.  Issued by ONE thread.
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-#define SA_WORDS_PER_THREAD (SA_STAGE_WORDS / SA_TERM_THREADS)
-
 template <int MODE, bool ALL_DOCS, bool FILTER>
-__global__ void __launch_bounds__(SA_TERM_THREADS, 5)
+__global__ void __launch_bounds__(SA_TERM_THREADS, 6)
 term_tile_kernel(const TermBatchArgs a) {
-    __shared__ __align__(128) u64 s_words[SA_STAGE_WORDS + 2];
     __shared__ __align__(16) float s_out[SA_TILE_DOCS];
-    __shared__ __align__(8) u64 s_bar;
     __shared__ u32 s_range[2];
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
     __shared__ u32 s_ncand;
@@ -120,89 +90,85 @@ term_tile_kernel(const TermBatchArgs a) {
     const u32 tile_doc0 = tile * SA_TILE_DOCS;                       // local doc index
     const u32 tile_doc0_abs = (u32)a.doc_base + tile_doc0;           // as stored in the words
 
-    // 1. posting slice [lo, hi) of this tile; thread 0 starts the TMA copy of its first chunk
-    //    into shared memory while everybody zeroes the score tile.
+    // 1. zero the tile; posting slice [lo, hi) of this tile
+#pragma unroll
+    for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
+        reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
     u32 lo, hi;
-    const bool has_dir = tq.dir_off != SA_NO_DIR;                     // CTA-uniform
-    if (has_dir) {
+    if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
         const u32 *dir = a.tile_dir + tq.dir_off + tile;
         lo = __ldg(dir);
         hi = __ldg(dir + 1);
+        __syncthreads();
     } else {
-        lo = hi = 0;
         if (warp < 2) {
             u64 key = (u64)tile_doc0_abs + (warp ? SA_TILE_DOCS : 0);
             u64 r = warp_lower_bound_shifted(words, 0, n_words, key, SA_KEY_SHIFT);
             if (lane == 0) s_range[warp] = (u32)r;
         }
-    }
-    // chunk c covers list indices [cs, cs + n); the copy starts at an even ABSOLUTE word index
-    auto issue_chunk = [&](u32 cs) {
-        const u32 n = min((u32)SA_STAGE_WORDS, hi - cs);
-        const u64 abs0 = tq.word_off + cs;
-        const u32 d = (u32)(abs0 & 1);
-        const u32 n_copy = (d + n + 1) & ~1u;
-        tma_load_1d(s_words, a.words + (abs0 - d), n_copy * 8, &s_bar);
-    };
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        if (has_dir && hi > lo) issue_chunk(lo);
-    }
-#pragma unroll
-    for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
-        reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    if (!has_dir) {
+        __syncthreads();
         lo = s_range[0];
         hi = s_range[1];
-        if (tid == 0 && hi > lo) issue_chunk(lo);
     }
 
-    // 2. process the slice chunk by chunk from shared memory.  Words are sorted by doc, so the
-    //    words of one doc are adjacent: the thread holding the FIRST word of a doc ("head") sums
-    //    the popcounts of the doc's run.  All norm gathers of a chunk are issued before any score
-    //    is computed (memory-level parallelism instead of one dependent load per iteration).
+    // 2. stream the slice.  Each warp takes windows of 30 owned words and loads 32 (two look-ahead
+    //    lanes), so "is the previous / next word the same doc?" is a register shuffle with no
+    //    warp-edge special case.  Words are sorted by doc: the thread holding the FIRST word of a
+    //    doc ("head") sums the doc's run (<= 3 words via shuffles, longer runs by look-ahead
+    //    loads).  SA_TERM_UNROLL windows are loaded before any is processed, and the heads' norm
+    //    gathers are issued back to back before any score is computed (memory-level parallelism).
     u32 my_max = 0;
     const float *__restrict__ norm = a.norm + tile_doc0;
-    u32 parity = 0;
-    for (u32 cs = lo; cs < hi; cs += SA_STAGE_WORDS) {                // CTA-uniform trip count
-        const u32 n = min((u32)SA_STAGE_WORDS, hi - cs);
-        const u32 d = (u32)((tq.word_off + cs) & 1);
-        const u32 n_smem = (d + n + 1) & ~1u;                          // words present in s_words
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-
-        u32 pk[SA_WORDS_PER_THREAD];                                   // rel << 18 | tf, or ~0
-        float nr[SA_WORDS_PER_THREAD];
+    constexpr u32 OWN = 30;
+    constexpr u32 STEP = (SA_TERM_THREADS / 32) * OWN * SA_TERM_UNROLL;
+    for (u32 base = lo; base < hi; base += STEP) {                    // CTA-uniform trip count
+        u64 w[SA_TERM_UNROLL];
 #pragma unroll
-        for (int u = 0; u < SA_WORDS_PER_THREAD; u++) {
-            const u32 x = tid + u * SA_TERM_THREADS;                   // chunk-local index
-            pk[u] = 0xFFFFFFFFu;
+        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+            const u32 i = base + (u * (SA_TERM_THREADS / 32) + warp) * OWN + lane;
+            // look-ahead lanes may read into the next tile (another doc) but never past the list
+            w[u] = (i < n_words && i < hi + 2) ? __ldg(words + i) : ~0ull;
+        }
+        u32 pk[SA_TERM_UNROLL];                                       // rel << 18 | tf, ~0 = not a head
+        float nr[SA_TERM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+            const u32 s = base + (u * (SA_TERM_THREADS / 32) + warp) * OWN;   // window start (warp-uniform)
+            const u32 i = s + lane;
+            const u32 rel = (u32)(w[u] >> SA_KEY_SHIFT) - tile_doc0_abs;  // >= 2^27 for the ~0 filler
+            u32 pc = (u32)__popcll(w[u] & SA_LSB_MASK);
+            if (FILTER && !payload_keep(w[u], a.min_payload, a.max_payload)) pc = 0;
+            const u32 packed = (rel << 5) | pc;                        // pc <= 18
+            u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
+            const u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
+            const u32 next2 = __shfl_down_sync(0xffffffffu, packed, 2);
+            if (lane == 0) {
+                prev = ~0u;                                           // s == lo: previous word is another tile's
+                if (s > lo && s < hi) prev = ((u32)(__ldg(words + s - 1) >> SA_KEY_SHIFT) - tile_doc0_abs) << 5;
+            }
+            pk[u] = ~0u;
             nr[u] = 0.0f;
-            if (x < n) {
-                const u32 sx = x + d;
-                const u64 w = s_words[sx];
-                const u32 rel = (u32)(w >> SA_KEY_SHIFT) - tile_doc0_abs;
-                bool head;
-                if (x == 0 && cs == lo) head = true;     // the previous word belongs to another tile (or term)
-                else if (sx > 0) head = ((u32)(s_words[sx - 1] >> SA_KEY_SHIFT) - tile_doc0_abs) != rel;
-                else head = ((u32)(__ldg(words + cs - 1) >> SA_KEY_SHIFT) - tile_doc0_abs) != rel;
-                if (head && rel < SA_TILE_DOCS) {
-                    u32 tf = (FILTER && !payload_keep(w, a.min_payload, a.max_payload)) ? 0u : (u32)__popcll(w & SA_LSB_MASK);
-                    for (u32 j = cs + x + 1; j < n_words; j++) {       // the rest of the doc's run
-                        const u32 sj = j - cs + d;
-                        const u64 w2 = (sj < n_smem) ? s_words[sj] : __ldg(words + j);
-                        if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
-                        if (!(FILTER && !payload_keep(w2, a.min_payload, a.max_payload))) tf += (u32)__popcll(w2 & SA_LSB_MASK);
+            const bool owned = lane < OWN && i < hi;
+            if (owned && (prev >> 5) != rel && rel < SA_TILE_DOCS) {
+                u32 tf = pc;
+                if ((next >> 5) == rel) {
+                    tf += next & 31u;
+                    if ((next2 >> 5) == rel) {
+                        tf += next2 & 31u;
+                        for (u32 j = i + 3; j < n_words; j++) {        // runs of >= 4 words (rare)
+                            const u64 w2 = __ldg(words + j);
+                            if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
+                            if (!(FILTER && !payload_keep(w2, a.min_payload, a.max_payload))) tf += (u32)__popcll(w2 & SA_LSB_MASK);
+                        }
                     }
-                    pk[u] = (rel << 18) | tf;
-                    if (MODE == TERM_MODE_SCORE && !ALL_DOCS && tf) nr[u] = __ldg(norm + rel);
                 }
+                pk[u] = (rel << 18) | tf;
+                if (MODE == TERM_MODE_SCORE && !ALL_DOCS && tf) nr[u] = __ldg(norm + rel);
             }
         }
 #pragma unroll
-        for (int u = 0; u < SA_WORDS_PER_THREAD; u++) {
-            if (pk[u] != 0xFFFFFFFFu) {
+        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+            if (pk[u] != ~0u) {
                 const u32 rel = pk[u] >> 18, tf = pk[u] & 0x3FFFFu;
                 float v;
                 if (MODE == TERM_MODE_TF || ALL_DOCS) {
@@ -216,10 +182,6 @@ term_tile_kernel(const TermBatchArgs a) {
                 }
                 s_out[rel] = v;
             }
-        }
-        if (cs + SA_STAGE_WORDS < hi) {                                // more chunks: refill the stage
-            __syncthreads();
-            if (tid == 0) issue_chunk(cs + SA_STAGE_WORDS);
         }
     }
 

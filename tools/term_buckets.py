@@ -17,7 +17,10 @@ h = dev.handle
 print('upload', time.time()-t0, flush=True)
 avgdl = float(np.mean(host.doc_lens))
 Q, k = 128, 10
+only = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else None
 for b, p in enumerate(synth.DF_BUCKETS):
+    if only is not None and b not in only:
+        continue
     tids = np.asarray([spec.term_index[f"b{b}_{j % 8}"] for j in range(Q)], dtype=np.uint32)
     df = host.term_lengths[tids]  # ~ words
     idf = np.asarray([compute_idf(n_docs, np.asarray([max(1, int(x))])) for x in df], dtype=np.float32)
