@@ -28,6 +28,7 @@
 // df bucket (profiles/README.md): the scan is bound by instruction issue on dense terms and by the
 // dense 4N write otherwise, not by load latency.
 #include <algorithm>
+#include <type_traits>
 
 #include "sa_term.cuh"
 
@@ -120,19 +121,20 @@ term_tile_kernel(const TermBatchArgs a) {
     u32 my_max = 0;
     const float *__restrict__ norm = a.norm + tile_doc0;
     constexpr u32 OWN = 30;
-    constexpr u32 STEP = (SA_TERM_THREADS / 32) * OWN * SA_TERM_UNROLL;
-    for (u32 base = lo; base < hi; base += STEP) {                    // CTA-uniform trip count
-        u64 w[SA_TERM_UNROLL];
+    constexpr u32 WIN = (SA_TERM_THREADS / 32) * OWN;                  // words per CTA pass (240)
+    auto windows = [&](auto unroll_tag, const u32 base) {
+        constexpr int UN = decltype(unroll_tag)::value;
+        u64 w[UN];
 #pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+        for (int u = 0; u < UN; u++) {
             const u32 i = base + (u * (SA_TERM_THREADS / 32) + warp) * OWN + lane;
             // look-ahead lanes may read into the next tile (another doc) but never past the list
             w[u] = (i < n_words && i < hi + 2) ? __ldg(words + i) : ~0ull;
         }
-        u32 pk[SA_TERM_UNROLL];                                       // rel << 18 | tf, ~0 = not a head
-        float nr[SA_TERM_UNROLL];
+        u32 pk[UN];                                       // rel << 18 | tf, ~0 = not a head
+        float nr[UN];
 #pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+        for (int u = 0; u < UN; u++) {
             const u32 s = base + (u * (SA_TERM_THREADS / 32) + warp) * OWN;   // window start (warp-uniform)
             const u32 i = s + lane;
             const u32 rel = (u32)(w[u] >> SA_KEY_SHIFT) - tile_doc0_abs;  // >= 2^27 for the ~0 filler
@@ -167,7 +169,7 @@ term_tile_kernel(const TermBatchArgs a) {
             }
         }
 #pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++) {
+        for (int u = 0; u < UN; u++) {
             if (pk[u] != ~0u) {
                 const u32 rel = pk[u] >> 18, tf = pk[u] & 0x3FFFFu;
                 float v;
@@ -183,13 +185,24 @@ term_tile_kernel(const TermBatchArgs a) {
                 s_out[rel] = v;
             }
         }
+    };
+    // CTA-uniform schedule: big slices in 4-window passes, the remainder (and small tiles) in
+    // single-window passes so sparse tiles do not pay for empty windows.
+    u32 base = lo;
+    while (base < hi && hi - base > WIN) {
+        windows(std::integral_constant<int, SA_TERM_UNROLL>{}, base);
+        base += WIN * SA_TERM_UNROLL;
+    }
+    while (base < hi) {
+        windows(std::integral_constant<int, 1>{}, base);
+        base += WIN;
     }
 
     // 3. top-k.  A tile with no more words than candidate slots needs no bound: every positive
     //    score fits.  Otherwise each warp publishes its largest thread maxima and every warp
     //    derives the same tile bound; scores >= bound are this tile's candidates.
     const u32 k = a.topk.k;
-    const bool need_bound = k && (hi - lo) > a.topk.slots;          // CTA-uniform
+    const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
     if (need_bound) {
         const u32 M = (k <= 10) ? 4u : 8u;
         u32 v = my_max;

@@ -67,12 +67,38 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
             s_keys[g] = m;
         }
     }
-    u32 g2 = 2;
-    while (g2 < G) g2 <<= 1;
-    for (u32 i = G + threadIdx.x; i < g2; i += blockDim.x) s_keys[i] = 0ull;
     __syncthreads();
-    bitonic_sort_desc_smem(s_keys, g2);
-    u64 thr = (k - 1 < g2) ? s_keys[k - 1] : 0ull;     // 0 => fewer than k groups have a candidate
+    // k-th largest of the G group maxima by an 8-bit MSB radix select in shared memory (cheaper
+    // than sorting them); zeros (groups without candidates) never win.
+    u64 thr = 0ull;
+    {
+        if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
+        __syncthreads();
+        bool enough = true;
+        for (int shift = 56; shift >= 0 && enough; shift -= 8) {
+            for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            const u64 prefix = s_prefix;
+            for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+                u64 key = s_keys[g];
+                bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+                if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                u32 rem = s_krem, acc = 0;
+                int b = 255;
+                for (; b > 0; b--) {
+                    if (acc + s_hist[b] >= rem) break;
+                    acc += s_hist[b];
+                }
+                s_krem = rem - acc;
+                s_prefix = prefix | ((u64)b << shift);
+            }
+            __syncthreads();
+        }
+        thr = s_prefix;                  // 0 when fewer than k groups hold a candidate
+    }
     if (thr == 0ull) thr = 1ull;
     __syncthreads();
 
