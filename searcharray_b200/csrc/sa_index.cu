@@ -429,6 +429,7 @@ static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_o
     a.mode = TERM_MODE_SCORE;
     a.topk.tile_cand = ix->cand.as<u64>();
     a.topk.tile_cnt = (u32 *)(a.topk.tile_cand + (u64)Q * T * slots);
+    a.topk.tile_max = a.topk.tile_cnt + (u64)Q * T;
     a.topk.overflow = d_overflow;
     a.topk.n_tiles = T;
     a.topk.slots = slots;
@@ -439,7 +440,7 @@ static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_o
 }
 
 static size_t cand_bytes(const sa_index *ix, u32 Q, u32 slots) {
-    return (size_t)Q * n_tiles_of(ix) * ((size_t)slots * sizeof(u64) + sizeof(u32)) + 64;
+    return (size_t)Q * n_tiles_of(ix) * ((size_t)slots * sizeof(u64) + 2 * sizeof(u32)) + 64;
 }
 
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,

@@ -80,7 +80,7 @@ term_tile_kernel(const TermBatchArgs a) {
     __shared__ __align__(16) float s_out[SA_TILE_DOCS];
     __shared__ u32 s_range[2];
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
-    __shared__ u32 s_ncand;
+    __shared__ u32 s_ncand, s_tile_max;
 
     const u32 q = blockIdx.y;
     const u32 tile = blockIdx.x;
@@ -211,7 +211,7 @@ term_tile_kernel(const TermBatchArgs a) {
             if (lane == r) s_top[warp * 8 + r] = m;
         }
     }
-    if (k && tid == 0) s_ncand = 0;
+    if (k && tid == 0) { s_ncand = 0; s_tile_max = 0; }
     __syncthreads();
     float thr_f = 0.0f;
     if (k) {
@@ -223,6 +223,7 @@ term_tile_kernel(const TermBatchArgs a) {
     if (k) my_cand = a.topk.tile_cand + ((u64)q * a.topk.n_tiles + tile) * a.topk.slots;
 
     // 4. flush the tile: 16-byte streaming stores (the padded buffer makes the tile always in bounds)
+    u32 cand_max = 0;
     float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
 #pragma unroll
     for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
@@ -251,16 +252,20 @@ term_tile_kernel(const TermBatchArgs a) {
                         if (slot < a.topk.slots)
                             my_cand[slot] = ((u64)__float_as_uint(vs[e]) << 32) |
                                             (u64)(0xFFFFFFFFu - (tile_doc0 + g * 4 + e));
+                        cand_max = max(cand_max, __float_as_uint(vs[e]));
                     }
                 }
             }
         }
     }
     if (k) {
+        if (cand_max) atomicMax(&s_tile_max, cand_max);
         __syncthreads();
         if (tid == 0) {
-            u32 n = s_ncand;
-            a.topk.tile_cnt[(u64)q * a.topk.n_tiles + tile] = min(n, a.topk.slots);
+            const u32 n = s_ncand;
+            const u64 t_idx = (u64)q * a.topk.n_tiles + tile;
+            a.topk.tile_cnt[t_idx] = min(n, a.topk.slots);
+            a.topk.tile_max[t_idx] = s_tile_max;
             if (n > a.topk.slots) a.topk.overflow[q] = 1u;
         }
     }

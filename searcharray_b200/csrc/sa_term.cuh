@@ -13,6 +13,7 @@ enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
 // (query, tile) CTA owns `slots` candidate slots.
 struct TopkCtx {
     u32 *tile_cnt;     // [Q][n_tiles] candidates written by the tile's CTA (<= slots)
+    u32 *tile_max;     // [Q][n_tiles] score bits of the tile's best candidate (0 = none)
     u64 *tile_cand;    // [Q][n_tiles][slots] key = score_bits << 32 | (0xFFFFFFFF - local_doc)
     u32 *overflow;     // [Q] set when some tile had more than `slots` candidates
     u32 n_tiles;

@@ -28,16 +28,30 @@ __device__ void bitonic_sort_desc_smem(u64 *s, u32 n_pow2) {
     }
 }
 
-// visit every candidate key of query q (tiles strided over threads)
+// visit every candidate key of query q whose tile can hold a key with score bits >= min_score
 template <typename F>
-__device__ __forceinline__ void for_each_candidate(const TopkCtx &t, u32 q, F f) {
+__device__ __forceinline__ void for_each_candidate(const TopkCtx &t, u32 q, u32 min_score, F f) {
     const u32 *cnt = t.tile_cnt + (u64)q * t.n_tiles;
+    const u32 *tmax = t.tile_max + (u64)q * t.n_tiles;
     const u64 *cand = t.tile_cand + (u64)q * t.n_tiles * t.slots;
     for (u32 tile = threadIdx.x; tile < t.n_tiles; tile += blockDim.x) {
+        if (tmax[tile] < min_score) continue;
         const u32 n = cnt[tile];
         const u64 *c = cand + (u64)tile * t.slots;
         for (u32 j = 0; j < n; j++) f(c[j]);
     }
+}
+
+// thread 0: walk the 256-bin histogram from the top until `rem` keys are covered
+__device__ __forceinline__ void radix_pick(const u32 *hist, u32 &rem, int &bin) {
+    u32 acc = 0;
+    int b = 255;
+    for (; b > 0; b--) {
+        if (acc + hist[b] >= rem) break;
+        acc += hist[b];
+    }
+    rem -= acc;
+    bin = b;
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
@@ -51,62 +65,52 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
     const u32 k = t.k;
     const u32 T = t.n_tiles;
 
-    // A. a tight valid threshold: the k-th largest of the per-tile-group maxima (distinct docs)
-    const u32 gs = (T + SEL_SMEM_KEYS - 1) / SEL_SMEM_KEYS;          // tiles per group
+    // A. a tight valid threshold: the k-th largest of the per-tile(-group) best scores (they
+    //    belong to distinct docs).  The tile maxima were written by the scoring kernel, so this
+    //    is one coalesced read of 4*T bytes; 4-pass 8-bit radix select in shared memory.
+    u32 *s_max = reinterpret_cast<u32 *>(s_keys);                   // [G] reuse (2 * SEL_SMEM_KEYS u32)
+    const u32 GMAX = 2 * SEL_SMEM_KEYS;
+    const u32 gs = (T + GMAX - 1) / GMAX;                            // tiles per group
     const u32 G = (T + gs - 1) / gs;
     {
-        const u32 *cnt = t.tile_cnt + (u64)q * T;
-        const u64 *cand = t.tile_cand + (u64)q * T * t.slots;
+        const u32 *tmax = t.tile_max + (u64)q * T;
         for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
-            u64 m = 0;
-            for (u32 tile = g * gs; tile < min(T, (g + 1) * gs); tile++) {
-                const u32 n = cnt[tile];
-                const u64 *c = cand + (u64)tile * t.slots;
-                for (u32 j = 0; j < n; j++) m = max(m, c[j]);
-            }
-            s_keys[g] = m;
+            u32 m = 0;
+            for (u32 tile = g * gs; tile < min(T, (g + 1) * gs); tile++) m = max(m, tmax[tile]);
+            s_max[g] = m;
         }
     }
+    if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
     __syncthreads();
-    // k-th largest of the G group maxima by an 8-bit MSB radix select in shared memory (cheaper
-    // than sorting them); zeros (groups without candidates) never win.
-    u64 thr = 0ull;
-    {
-        if (threadIdx.x == 0) { s_prefix = 0; s_krem = k; }
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
-        bool enough = true;
-        for (int shift = 56; shift >= 0 && enough; shift -= 8) {
-            for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
-            __syncthreads();
-            const u64 prefix = s_prefix;
-            for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
-                u64 key = s_keys[g];
-                bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
-                if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                u32 rem = s_krem, acc = 0;
-                int b = 255;
-                for (; b > 0; b--) {
-                    if (acc + s_hist[b] >= rem) break;
-                    acc += s_hist[b];
-                }
-                s_krem = rem - acc;
-                s_prefix = prefix | ((u64)b << shift);
-            }
-            __syncthreads();
+        const u32 prefix = (u32)s_prefix;
+        for (u32 g = threadIdx.x; g < G; g += blockDim.x) {
+            u32 key = s_max[g];
+            bool match = (shift == 24) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+            if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
         }
-        thr = s_prefix;                  // 0 when fewer than k groups hold a candidate
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u32 rem = s_krem;
+            int b;
+            radix_pick(s_hist, rem, b);
+            s_krem = rem;
+            s_prefix = (u64)(prefix | ((u32)b << shift));
+        }
+        __syncthreads();
     }
-    if (thr == 0ull) thr = 1ull;
+    u32 thr_score = (u32)s_prefix;      // 0 when fewer than k tile groups hold a candidate
+    if (thr_score == 0) thr_score = 1;
     __syncthreads();
 
-    // B. survivors >= thr (a superset of the true top-k, normally ~k of them)
+    // B. survivors with score >= thr_score (a superset of the true top-k, normally ~k of them);
+    //    tiles whose best score is below the threshold are skipped without touching their slots
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for_each_candidate(t, q, [&](u64 key) {
-        if (key >= thr) {
+    for_each_candidate(t, q, thr_score, [&](u64 key) {
+        if ((u32)(key >> 32) >= thr_score) {
             u32 slot = atomicAdd(&s_n, 1u);
             if (slot < SEL_SMEM_KEYS) s_keys[slot] = key;
         }
@@ -129,20 +133,17 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
             for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
             __syncthreads();
             const u64 prefix = s_prefix;
-            for_each_candidate(t, q, [&](u64 key) {
-                if (key < thr) return;
+            for_each_candidate(t, q, thr_score, [&](u64 key) {
+                if ((u32)(key >> 32) < thr_score) return;
                 bool match = (shift == 56) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
                 if (match) atomicAdd(&s_hist[(key >> shift) & 255], 1u);
             });
             __syncthreads();
             if (threadIdx.x == 0) {
-                u32 rem = s_krem, acc = 0;
-                int b = 255;
-                for (; b > 0; b--) {
-                    if (acc + s_hist[b] >= rem) break;
-                    acc += s_hist[b];
-                }
-                s_krem = rem - acc;
+                u32 rem = s_krem;
+                int b;
+                radix_pick(s_hist, rem, b);
+                s_krem = rem;
                 s_prefix = prefix | ((u64)b << shift);
             }
             __syncthreads();
@@ -150,7 +151,7 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
         const u64 kth = s_prefix;
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        for_each_candidate(t, q, [&](u64 key) {
+        for_each_candidate(t, q, thr_score, [&](u64 key) {
             if (key >= kth) {
                 u32 slot = atomicAdd(&s_n, 1u);
                 if (slot < SEL_SMEM_KEYS) s_keys[slot] = key;
