@@ -383,6 +383,24 @@ def bench_ours(args, rank, world):
             del ref
         cpu["gpu_topk_mismatches_in_16"] = bad
 
+    verify = None
+    if rank == 0 and args.verify:
+        from oracle import ops as oops, search as osearch
+        from searcharray_b200 import synth
+        from searcharray_b200.shard import shard_topk_keys, unpack_keys
+        full, _, _ = (host, lo, hi) if world == 1 else synth.generate_shard(spec, 0, 1)
+        bad = 0
+        for qi in range(min(args.verify, Q)):
+            t = int(term_ids[qi])
+            ids, tfs = osearch.termfreqs_sparse(full.term_words(t))
+            sc = tfs.copy()
+            oops.bm25_score(sc, full.doc_lens[ids.astype(np.int64)], avgdl, float(idf[qi]), K1, B)
+            wd, ws = unpack_keys(shard_topk_keys(ids, sc, k))
+            if not (np.array_equal(wd, out_docs[qi]) and np.array_equal(ws.view(np.uint32), out_scores[qi].view(np.uint32))):
+                bad += 1
+        verify = {"queries_checked": min(args.verify, Q), "mismatches": bad}
+        log("verify:", verify)
+
     if rank == 0:
         line = {
             "metric": "queries/sec (single-term BM25 + top-k) on 10M-doc synthetic MSMARCO",
@@ -397,6 +415,7 @@ def bench_ours(args, rank, world):
             "cpu_baseline": cpu,
             "e2e_dense": e2e_dense,
             "topk_overflow_reruns": int(overflow),
+            "verify": verify,
         }
         print(json.dumps(line), flush=True)
     dev.close()
@@ -413,6 +432,9 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--ref-sample", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", type=int, default=0,
+                    help="rank 0 re-generates the FULL corpus and checks this many queries' global top-k "
+                         "against the CPU oracle (parity of the sharded / all-gathered path)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
