@@ -216,15 +216,28 @@ def bench_ours(args, rank, world):
     h = dev.handle
 
     if world > 1:
-        import torch.distributed as dist         # plumbing only: rendezvous for the NCCL unique id
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        # Rendezvous for the NCCL unique id without any framework: all ranks of one launch share a
+        # node (contract: --nnodes=1) and a parent (the torchrun agent), so rank 0 publishes the id
+        # in a file keyed by MASTER_PORT + parent pid and the others poll for it.
+        key = f"/tmp/sa_b200_uid_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.bin"
         uid = (ctypes.c_char * 128)()
         if rank == 0:
             _lib.check(L.sa_comm_unique_id(uid))
-        box = [bytes(uid)]
-        dist.broadcast_object_list(box, src=0)
-        uid = (ctypes.c_char * 128).from_buffer_copy(box[0])
+            with open(key + ".tmp", "wb") as f:
+                f.write(bytes(uid))
+            os.replace(key + ".tmp", key)
+        else:
+            t_wait = time.time()
+            while not os.path.exists(key):
+                if time.time() - t_wait > 600:
+                    raise RuntimeError("timed out waiting for rank 0's NCCL id")
+                time.sleep(0.05)
+            with open(key, "rb") as f:
+                uid = (ctypes.c_char * 128).from_buffer_copy(f.read(128))
         _lib.check(L.sa_comm_init(h, uid, rank, world))
+        _lib.check(L.sa_comm_barrier(h))
+        if rank == 0:
+            os.remove(key)
 
     def barrier():
         if world > 1:

@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]   # NCCL is dlopen'ed (sa_comm.cu)
         subprocess.check_call(cmd)
     return LIB
 

@@ -1,9 +1,57 @@
 // sa_comm.cu -- the one collective on the scoring path: every rank
 // owns a contiguous doc-id range, scores its shard, and the per-shard top-k lists are
 // exchanged with a single ncclAllGather per query batch, then merged on the device.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is bound at run time (see nccl_api)
 
 #include "sa_term.cuh"
+
+// NCCL is dlopen'ed on first use instead of being a link-time dependency: PyTorch bundles its own
+// libnccl.so.2 under the same SONAME, and whichever copy a process loads first wins.  Binding
+// lazily means this library never forces the (older) system copy on a process that also imports
+// torch, and works without torch too.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok = false;
+};
+
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.AllReduce &&
+                 api.GetErrorString;
+    });
+    return &api;
+}
+
+#define ncclGetUniqueId nccl_api()->GetUniqueId
+#define ncclCommInitRank nccl_api()->CommInitRank
+#define ncclCommDestroy nccl_api()->CommDestroy
+#define ncclAllGather nccl_api()->AllGather
+#define ncclAllReduce nccl_api()->AllReduce
+#define ncclGetErrorString nccl_api()->GetErrorString
+#define SA_NEED_NCCL()                                                              \
+    do {                                                                            \
+        if (!nccl_api()->ok) {                                                      \
+            sa_set_error("libnccl.so.2 could not be loaded (%s)", dlerror());       \
+            return SA_ERR_NCCL;                                                     \
+        }                                                                           \
+    } while (0)
 
 #define SA_NCCL(call)                                                                  \
     do {                                                                               \
@@ -16,6 +64,7 @@
 
 extern "C" int sa_comm_unique_id(void *id128_out) {
     SA_CHECK(id128_out, "id buffer is NULL");
+    SA_NEED_NCCL();
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
     SA_NCCL(ncclGetUniqueId(&id));
@@ -26,6 +75,7 @@ extern "C" int sa_comm_unique_id(void *id128_out) {
 extern "C" int sa_comm_init(sa_index *ix, const void *id128, int rank, int world_size) {
     SA_CHECK(ix && id128, "NULL argument");
     SA_CHECK(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world");
+    SA_NEED_NCCL();
     std::lock_guard<std::mutex> g(ix->mu);
     SA_CUDA(cudaSetDevice(ix->device));
     ncclUniqueId id;
