@@ -216,6 +216,10 @@ def bench_ours(args, rank, world):
     h = dev.handle
 
     if world > 1:
+        # NCCL_DEBUG=VERSION (some images default to it) prints a banner on STDOUT, which would
+        # break the one-JSON-line contract
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         # Rendezvous for the NCCL unique id without any framework: all ranks of one launch share a
         # node (contract: --nnodes=1) and a parent (the torchrun agent), so rank 0 publishes the id
         # in a file keyed by MASTER_PORT + parent pid and the others poll for it.
