@@ -354,6 +354,62 @@ def bench_ours(args, rank, world):
                 "topk_select_ms_per_step": stats.topk_kernel_ms / prof_steps,
                 "kernel_share_of_step": term_ms / (dev_ms / args.steps)}
 
+    # ---- phrase workload (BASELINE configs[2]: 4-term phrase, slop 0) as an extra block
+    phrase = None
+    if args.phrase_queries > 0:
+        from searcharray_b200 import synth
+        pq_names = synth.phrase_queries(spec, args.phrase_queries)
+        p_terms = np.asarray([spec.term_index[t] for ph in pq_names for t in ph], dtype=np.uint32)
+        p_starts = np.arange(0, 4 * len(pq_names) + 1, 4, dtype=np.uint32)
+        p_idf = np.asarray([float(np.sum(np.log(1 + (args.docs - df[[spec.term_index[t] for t in ph]].astype(np.float64) + 0.5)
+                                                / (df[[spec.term_index[t] for t in ph]].astype(np.float64) + 0.5))))
+                            for ph in pq_names], dtype=np.float32)
+        PQ = len(pq_names)
+        p_docs = np.empty((PQ, k), dtype=np.uint32)
+        p_scores = np.empty((PQ, k), dtype=np.float32)
+
+        def p_upload():
+            _lib.check(L.sa_batch_upload(h, _lib.p_u32(p_terms), _lib.p_u32(p_starts), _lib.p_f32(p_idf), PQ, 0,
+                                         float(avgdl), K1, B, k))
+
+        def p_download():
+            if world > 1:
+                _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
+            else:
+                _lib.check(L.sa_batch_download(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
+            return n_over.value
+
+        p_redo = 0
+        for _ in range(3):
+            p_upload(); execute(); p_redo += p_download()
+        p_upload()
+        _lib.check(L.sa_stats_reset(h))
+        barrier()
+        _lib.check(L.sa_timer_start(h))
+        p_steps = max(2, args.steps)
+        for _ in range(p_steps):
+            execute()
+        _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
+        barrier()
+        p_ms = max_over_ranks(ms.value)
+        p_download()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(p_steps):
+            p_upload(); execute(); p_redo += p_download()
+        barrier()
+        p_e2e_s = max_over_ranks(time.perf_counter() - t0)
+        Wp = np.asarray([[host.term_lengths[spec.term_index[t]] for t in ph] for ph in pq_names], dtype=np.float64)
+        phrase = {"workload": "4-term phrase, slop 0 (BASELINE configs[2]), planted phrases, top-%d" % k,
+                  "queries_per_step": PQ, "value": p_steps * PQ / (p_ms / 1e3), "unit": "queries/s",
+                  "ms_per_step": p_ms / p_steps,
+                  "e2e": {"value": p_steps * PQ / p_e2e_s, "unit": "queries/s"},
+                  "mean_words_per_query_this_shard": float(np.mean(np.sum(Wp, axis=1))),
+                  "min_list_words_mean": float(np.mean(np.min(Wp, axis=1))),
+                  "repairs": int(p_redo),
+                  "matches_in_top1": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF))}
+        upload()          # restore the term batch for the sections below
+
     # ---- e2e_dense: the literal .score() drop-in, dense float32[N] to the host per query
     e2e_dense = None
     if rank == 0 and world == 1:
@@ -431,6 +487,7 @@ def bench_ours(args, rank, world):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e_dense": e2e_dense,
+            "phrase": phrase,
             "topk_overflow_reruns": int(overflow),
             "verify": verify,
         }
@@ -449,6 +506,7 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--ref-sample", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phrase-queries", type=int, default=256)
     ap.add_argument("--verify", type=int, default=0,
                     help="rank 0 re-generates the FULL corpus and checks this many queries' global top-k "
                          "against the CPU oracle (parity of the sharded / all-gathered path)")

@@ -5,6 +5,7 @@
 #include <cmath>
 
 #include "sa_term.cuh"
+#include "sa_phrase.cuh"
 
 // ------------------------------------------------------------------ error text
 static thread_local char g_err[1024] = "";
@@ -385,14 +386,32 @@ extern "C" int sa_score_term(sa_index *ix, uint32_t term_id, float idf, float av
 
 // ------------------------------------------------ batched, HBM-resident top-k
 // A prepared batch: query descriptors live in HBM; sa_batch_execute only enqueues kernels.
+// Queries are processed in chunks (bounded dense-vector memory).  Inside a chunk the term queries
+// take dense rows [0, nT) (one fused launch) and the phrase queries rows [nT, nT + nP) (phrase
+// kernel + tile scan); one select launch covers the chunk and writes each result at its
+// original query index.
+struct BatchChunk {
+    u32 row0 = 0;          // first row (in the permuted "row space") of this chunk
+    u32 n_term = 0, n_phrase = 0;
+    u32 term0 = 0, phrase0 = 0;     // offsets into the batch-wide TermQuery / PhraseQuery arrays
+    Bm25Params params;
+    u32 phrase_chunks = 1;          // doc-range chunks per phrase query
+    u64 arena_words = 64;
+};
+
 struct BatchState {
     u32 nq = 0, k = 0, slots = 0, chunk = 0;
     float avg_doc_len = 0, k1 = 0, b = 0;
     bool ready = false;
-    std::vector<TermQuery> qs;
-    std::vector<Bm25Params> chunk_params;     // per chunk (sparse_ok must hold for every idf in it)
-    DevBuf d_queries;                          // TermQuery[nq]
-    DevBuf d_meta;                             // u32 overflow[nq]
+    std::vector<TermQuery> tqs;               // all term queries, chunk by chunk
+    std::vector<PhraseQuery> pqs;             // all phrase queries, chunk by chunk
+    std::vector<u32> row_query;               // row -> original query index
+    std::vector<u32> term_query, phrase_query;  // index in tqs / pqs -> original query index
+    std::vector<u32> phrase_missing;          // 1 = a term is unknown: result stays empty
+    std::vector<BatchChunk> chunks;
+    DevBuf d_tq, d_pq, d_row_query;
+    DevBuf d_meta;                            // u32 overflow[nq] (row space)
+    DevBuf d_pstats;                          // PhraseStats[#phrase queries]
 };
 
 static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
@@ -407,12 +426,24 @@ static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
 
 static u32 n_tiles_of(const sa_index *ix) { return (u32)((ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS); }
 
-// Enqueue scoring + candidate collection + select for Q queries (async).  ix->cand must hold
-// Q * n_tiles * (slots * 8 + 4) bytes.
-static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_overflow,
-                              u32 Q, const Bm25Params &p, u32 k, u32 slots, u64 *d_keys) {
-    const u64 stride = padded_docs(ix->n_docs);
+static size_t cand_bytes(const sa_index *ix, u32 Q, u32 slots) {
+    return (size_t)Q * n_tiles_of(ix) * ((size_t)slots * sizeof(u64) + 2 * sizeof(u32)) + 64;
+}
+
+static TopkCtx make_topk_ctx(sa_index *ix, u32 Q, u32 slots, u32 k, u32 *d_overflow) {
     const u32 T = n_tiles_of(ix);
+    TopkCtx t;
+    t.tile_cand = ix->cand.as<u64>();
+    t.tile_cnt = (u32 *)(t.tile_cand + (u64)Q * T * slots);
+    t.tile_max = t.tile_cnt + (u64)Q * T;
+    t.overflow = d_overflow;
+    t.n_tiles = T;
+    t.slots = slots;
+    t.k = k;
+    return t;
+}
+
+static TermBatchArgs make_term_args(sa_index *ix, const TermQuery *d_queries, const Bm25Params &p, const TopkCtx &t) {
     TermBatchArgs a;
     memset(&a, 0, sizeof(a));
     a.words = ix->d_words;
@@ -421,34 +452,22 @@ static int enqueue_topk_chunk(sa_index *ix, const TermQuery *d_queries, u32 *d_o
     a.doc_base = ix->doc_base;
     a.queries = d_queries;
     a.out = ix->dense.as<float>();
-    a.out_stride = stride;
+    a.out_stride = padded_docs(ix->n_docs);
     a.bm25 = p;
     a.min_payload = 0;
     a.max_payload = SA_ALL_BITS;
     a.filter = 0;
     a.mode = TERM_MODE_SCORE;
-    a.topk.tile_cand = ix->cand.as<u64>();
-    a.topk.tile_cnt = (u32 *)(a.topk.tile_cand + (u64)Q * T * slots);
-    a.topk.tile_max = a.topk.tile_cnt + (u64)Q * T;
-    a.topk.overflow = d_overflow;
-    a.topk.n_tiles = T;
-    a.topk.slots = slots;
-    a.topk.k = k;
-    int rc;
-    if ((rc = launch_term_batch(ix, a, Q))) return rc;
-    return launch_topk_select(ix, a.topk, Q, ix->doc_base, d_keys);
-}
-
-static size_t cand_bytes(const sa_index *ix, u32 Q, u32 slots) {
-    return (size_t)Q * n_tiles_of(ix) * ((size_t)slots * sizeof(u64) + 2 * sizeof(u32)) + 64;
+    a.topk = t;
+    return a;
 }
 
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
                            const float *idf, uint32_t n_queries, uint32_t slop,
                            float avg_doc_len, float k1, float b, uint32_t k) {
-    (void)slop;
     SA_CHECK(ix && (n_queries == 0 || (terms && term_starts && idf)), "NULL argument");
     SA_CHECK(k >= 1 && k <= SA_TOPK_MAX, "k must be in [1, %d]", SA_TOPK_MAX);
+    SA_CHECK(slop == 0, "slop > 0 in a batch is not implemented yet");
     SA_CUDA(cudaSetDevice(ix->device));
     if (!ix->batch) ix->batch = new BatchState();
     BatchState &B = *ix->batch;
@@ -459,8 +478,8 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     B.avg_doc_len = avg_doc_len;
     B.k1 = k1;
     B.b = b;
-    B.qs.clear();
-    B.chunk_params.clear();
+    B.tqs.clear(); B.pqs.clear(); B.row_query.clear(); B.term_query.clear(); B.phrase_query.clear();
+    B.phrase_missing.clear(); B.chunks.clear();
     int rc;
     if ((rc = ix->topk_out.reserve(std::max<size_t>((size_t)n_queries * k * sizeof(u64), 256)))) return rc;
     if (n_queries == 0) { B.ready = true; return SA_OK; }
@@ -468,25 +487,72 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     // chunk so the dense score vectors of one chunk stay within ~4 GB of HBM
     u32 chunk = (u32)std::max<u64>(1, std::min<u64>(n_queries, (4ull << 30) / (stride * sizeof(float))));
     B.chunk = std::min<u32>(chunk, 65535);
-    for (u32 q = 0; q < n_queries; q++) {
-        SA_CHECK(term_starts[q + 1] - term_starts[q] == 1,
-                 "query %u: phrase queries in a batch are not supported yet", q);
-        u32 t = terms[term_starts[q]];
-        SA_CHECK(t == SA_NO_TERM || t < ix->n_terms, "term id %u out of range", t);
-        B.qs.push_back(make_term_query(ix, t, idf[q]));
-    }
+    u64 max_arena = 64;
     for (u32 q0 = 0; q0 < n_queries; q0 += B.chunk) {
-        Bm25Params p = make_bm25(ix, 1.0f, avg_doc_len, k1, b);
-        for (u32 q = q0; q < std::min(n_queries, q0 + B.chunk); q++)
-            if (!make_bm25(ix, idf[q], avg_doc_len, k1, b).sparse_ok) p.sparse_ok = 0;
-        B.chunk_params.push_back(p);
+        const u32 q1 = std::min(n_queries, q0 + B.chunk);
+        BatchChunk C;
+        C.row0 = (u32)B.row_query.size();
+        C.term0 = (u32)B.tqs.size();
+        C.phrase0 = (u32)B.pqs.size();
+        C.params = make_bm25(ix, 1.0f, avg_doc_len, k1, b);
+        for (int pass = 0; pass < 2; pass++) {               // term queries first, then phrases
+            for (u32 q = q0; q < q1; q++) {
+                const u32 nt = term_starts[q + 1] - term_starts[q];
+                SA_CHECK(nt >= 1 && nt <= SA_MAX_PHRASE_TERMS, "query %u: bad number of terms", q);
+                const u32 *tids = terms + term_starts[q];
+                for (u32 i = 0; i < nt; i++)
+                    SA_CHECK(tids[i] == SA_NO_TERM || tids[i] < ix->n_terms, "term id %u out of range", tids[i]);
+                if ((nt == 1) != (pass == 0)) continue;
+                if (!make_bm25(ix, idf[q], avg_doc_len, k1, b).sparse_ok) C.params.sparse_ok = 0;
+                B.row_query.push_back(q);
+                if (nt == 1) {
+                    B.tqs.push_back(make_term_query(ix, tids[0], idf[q]));
+                    B.term_query.push_back(q);
+                } else {
+                    PhraseQuery pq;
+                    memset(&pq, 0, sizeof(pq));
+                    pq.n_terms = nt;
+                    pq.idf = idf[q];
+                    u32 missing = 0;
+                    for (u32 i = 0; i < nt; i++) {
+                        if (tids[i] == SA_NO_TERM || ix->h_len[tids[i]] == 0) { missing = 1; continue; }
+                        pq.off[i] = ix->h_off[tids[i]];
+                        pq.len[i] = ix->h_len[tids[i]];
+                    }
+                    if (missing) for (u32 i = 0; i < nt; i++) pq.len[i] = 0;     // no pairs -> zeros
+                    sa_phrase_plan(pq, tids);
+                    B.pqs.push_back(pq);
+                    B.phrase_query.push_back(q);
+                    B.phrase_missing.push_back(missing);
+                }
+            }
+        }
+        C.n_term = (u32)B.tqs.size() - C.term0;
+        C.n_phrase = (u32)B.pqs.size() - C.phrase0;
+        if (C.n_phrase) {
+            u64 want = std::max<u64>(1, (u64)ix->num_sms * 16 / C.n_phrase);
+            C.phrase_chunks = (u32)std::max<u64>(1, std::min<u64>(want, std::max<u64>(1, ix->n_docs / 512)));
+            for (u32 i = 0; i < C.n_phrase; i++)
+                C.arena_words += sa_phrase_arena_words(B.pqs[C.phrase0 + i], C.phrase_chunks);
+            max_arena = std::max(max_arena, C.arena_words);
+        }
+        B.chunks.push_back(C);
     }
+    SA_CHECK(B.chunks.empty() || B.chunks[0].params.sparse_ok || B.pqs.empty(),
+             "phrase queries in a batch need ordinary BM25 parameters (k1 > 0, 0 <= b < 1, finite idf)");
     if ((rc = ix->dense.reserve((size_t)B.chunk * stride * sizeof(float)))) return rc;
     if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
-    if ((rc = B.d_queries.reserve((size_t)n_queries * sizeof(TermQuery)))) return rc;
+    if ((rc = B.d_tq.reserve(std::max<size_t>(B.tqs.size() * sizeof(TermQuery), 64)))) return rc;
+    if ((rc = B.d_pq.reserve(std::max<size_t>(B.pqs.size() * sizeof(PhraseQuery), 64)))) return rc;
+    if ((rc = B.d_row_query.reserve((size_t)n_queries * sizeof(u32)))) return rc;
     if ((rc = B.d_meta.reserve((size_t)n_queries * sizeof(u32)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(B.d_queries.p, B.qs.data(), (size_t)n_queries * sizeof(TermQuery),
-                            cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = B.d_pstats.reserve(std::max<size_t>(B.pqs.size() * sizeof(PhraseStats), 64)))) return rc;
+    if (!B.pqs.empty() && (rc = ix->phrase_scratch.reserve(max_arena * sizeof(u64) + 64))) return rc;
+    if (!B.tqs.empty())
+        SA_CUDA(cudaMemcpyAsync(B.d_tq.p, B.tqs.data(), B.tqs.size() * sizeof(TermQuery), cudaMemcpyHostToDevice, ix->stream));
+    if (!B.pqs.empty())
+        SA_CUDA(cudaMemcpyAsync(B.d_pq.p, B.pqs.data(), B.pqs.size() * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
+    SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, B.row_query.data(), (size_t)n_queries * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
     B.ready = true;
     return SA_OK;
 }
@@ -501,44 +567,98 @@ int sa_batch_execute_locked(sa_index *ix) {
         SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)B.nq * B.k * sizeof(u64), ix->stream));
         return SA_OK;
     }
+    const u64 stride = padded_docs(ix->n_docs);
     u32 *d_ovf = B.d_meta.as<u32>();
     SA_CUDA(cudaMemsetAsync(d_ovf, 0, (size_t)B.nq * sizeof(u32), ix->stream));
-    u32 ci = 0;
-    for (u32 q0 = 0; q0 < B.nq; q0 += B.chunk, ci++) {
-        const u32 Q = std::min(B.chunk, B.nq - q0);
-        int rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q0, d_ovf + q0, Q,
-                                    B.chunk_params[ci], B.k, B.slots, d_keys + (u64)q0 * B.k);
-        if (rc) return rc;
+    if (!B.pqs.empty())
+        SA_CUDA(cudaMemsetAsync(B.d_pstats.p, 0, B.pqs.size() * sizeof(PhraseStats), ix->stream));
+    int rc;
+    for (const BatchChunk &C : B.chunks) {
+        const u32 Q = C.n_term + C.n_phrase;
+        TopkCtx t = make_topk_ctx(ix, Q, B.slots, B.k, d_ovf + C.row0);
+        if (C.n_term) {
+            TermBatchArgs a = make_term_args(ix, B.d_tq.as<TermQuery>() + C.term0, C.params, t);
+            if ((rc = launch_term_batch(ix, a, C.n_term))) return rc;
+        }
+        if (C.n_phrase) {
+            float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;
+            unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
+            SA_CUDA(cudaMemsetAsync(rows, 0, (size_t)C.n_phrase * stride * sizeof(float), ix->stream));
+            SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
+            if ((rc = sa_phrase_enqueue(ix, B.d_pq.as<PhraseQuery>() + C.phrase0, B.d_pstats.as<PhraseStats>() + C.phrase0,
+                                        C.n_phrase, rows, stride, C.phrase_chunks, (u64 *)ix->phrase_scratch.p + 8,
+                                        d_used, C.arena_words, 1, C.params))) return rc;
+            if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, C.n_term, C.n_phrase, t))) return rc;
+        }
+        if ((rc = launch_topk_select(ix, t, Q, ix->doc_base, d_keys, B.d_row_query.as<u32>() + C.row0))) return rc;
     }
     return SA_OK;
 }
 
-// After execute: re-run (synchronously) the queries whose per-tile candidate slots overflowed.
+// Re-run one query exactly (synchronously): a tile overflowed its candidate slots, or a phrase's
+// same-term speculation was wrong.  Uses a slot per doc of the tile -- cannot overflow.
+static int redo_query(sa_index *ix, BatchState &B, bool is_phrase, u32 idx, u32 q) {
+    int rc;
+    const u64 stride = padded_docs(ix->n_docs);
+    if ((rc = ix->cand.reserve(cand_bytes(ix, 1, SA_TILE_DOCS)))) return rc;
+    SA_CUDA(cudaMemsetAsync(B.d_meta.p, 0, sizeof(u32), ix->stream));
+    TopkCtx t = make_topk_ctx(ix, 1, SA_TILE_DOCS, B.k, B.d_meta.as<u32>());
+    if (!is_phrase) {
+        Bm25Params p = make_bm25(ix, B.tqs[idx].idf, B.avg_doc_len, B.k1, B.b);
+        TermBatchArgs a = make_term_args(ix, B.d_tq.as<TermQuery>() + idx, p, t);
+        if ((rc = launch_term_batch(ix, a, 1))) return rc;
+    } else {
+        Bm25Params p = make_bm25(ix, B.pqs[idx].idf, B.avg_doc_len, B.k1, B.b);
+        std::vector<PhraseQuery> one(1, B.pqs[idx]);
+        PhraseDump nodump;
+        memset(&nodump, 0, sizeof(nodump));
+        if ((rc = sa_phrase_run_sync(ix, one, ix->d_words, 1, p, 0, nodump))) return rc;   // loops until the guess holds
+        B.pqs[idx] = one[0];
+        if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, 0, 1, t))) return rc;
+    }
+    SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, &q, sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = launch_topk_select(ix, t, 1, ix->doc_base, ix->topk_out.as<u64>(), B.d_row_query.as<u32>()))) return rc;
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    return SA_OK;
+}
+
+// After execute: repair (synchronously) the queries that need it.
 int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
     BatchState &B = *ix->batch;
     if (n_redone) *n_redone = 0;
     if (B.nq == 0 || ix->n_docs == 0 || B.avg_doc_len == 0.0f) return SA_OK;
     int rc;
-    if ((rc = sa_pinned_reserve(ix, std::max<size_t>((size_t)B.nq * sizeof(u32), 4096)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, B.d_meta.p, (size_t)B.nq * sizeof(u32), cudaMemcpyDeviceToHost, ix->stream));
+    const size_t ovf_bytes = (size_t)B.nq * sizeof(u32), st_bytes = B.pqs.size() * sizeof(PhraseStats);
+    if ((rc = sa_pinned_reserve(ix, std::max<size_t>(ovf_bytes + st_bytes, 4096)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, B.d_meta.p, ovf_bytes, cudaMemcpyDeviceToHost, ix->stream));
+    if (st_bytes)
+        SA_CUDA(cudaMemcpyAsync((char *)ix->h_pinned + ovf_bytes, B.d_pstats.p, st_bytes, cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
-    std::vector<u32> redo;
-    const u32 *ovf = (const u32 *)ix->h_pinned;
-    for (u32 q = 0; q < B.nq; q++) if (ovf[q]) redo.push_back(q);
-    if (redo.empty()) return SA_OK;
-    // a tile had more candidates than slots (massive ties / adversarial score layout): one
-    // query at a time with a slot for every doc of the tile -- cannot overflow, stays exact.
-    if ((rc = ix->cand.reserve(cand_bytes(ix, 1, SA_TILE_DOCS)))) return rc;
-    for (u32 q : redo) {
-        SA_CUDA(cudaMemsetAsync(B.d_meta.as<u32>() + q, 0, sizeof(u32), ix->stream));
-        Bm25Params p = make_bm25(ix, B.qs[q].idf, B.avg_doc_len, B.k1, B.b);
-        rc = enqueue_topk_chunk(ix, B.d_queries.as<TermQuery>() + q, B.d_meta.as<u32>() + q, 1, p, B.k,
-                                SA_TILE_DOCS, ix->topk_out.as<u64>() + (u64)q * B.k);
-        if (rc) return rc;
+    std::vector<u32> ovf((const u32 *)ix->h_pinned, (const u32 *)ix->h_pinned + B.nq);       // row space
+    std::vector<PhraseStats> st(B.pqs.size());
+    if (st_bytes) memcpy(st.data(), (char *)ix->h_pinned + ovf_bytes, st_bytes);
+    struct Redo { bool phrase; u32 idx, q; };
+    std::vector<Redo> redo;
+    for (const BatchChunk &C : B.chunks) {
+        for (u32 i = 0; i < C.n_term; i++)
+            if (ovf[C.row0 + i]) redo.push_back({false, C.term0 + i, B.term_query[C.term0 + i]});
+        for (u32 i = 0; i < C.n_phrase; i++) {
+            const u32 pi = C.phrase0 + i;
+            SA_CHECK(!st[pi].overflow, "phrase scratch arena exhausted (internal sizing error)");
+            PhraseQuery trial = B.pqs[pi];
+            bool ok = B.phrase_missing[pi] || sa_phrase_guess_ok(trial, st[pi]);
+            if (!ok || ovf[C.row0 + C.n_term + i]) redo.push_back({true, pi, B.phrase_query[pi]});
+        }
     }
-    SA_CUDA(cudaStreamSynchronize(ix->stream));
-    // the big buffer is only for repairs: give the batch its normal one back
+    if (redo.empty()) return SA_OK;
+    for (const Redo &r : redo)
+        if ((rc = redo_query(ix, B, r.phrase, r.idx, r.q))) return rc;
+    // the repair buffers are larger than the batch's: restore the normal ones and descriptors
     if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, B.row_query.data(), (size_t)B.nq * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+    if (!B.pqs.empty())
+        SA_CUDA(cudaMemcpyAsync(B.d_pq.p, B.pqs.data(), B.pqs.size() * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
     if (n_redone) *n_redone = (u32)redo.size();
     return SA_OK;
 }
@@ -661,8 +781,11 @@ extern "C" int sa_timer_stop(sa_index *ix, double *ms_out) {
 
 void sa_free_batch(sa_index *ix) {
     if (!ix->batch) return;
-    ix->batch->d_queries.release();
+    ix->batch->d_tq.release();
+    ix->batch->d_pq.release();
+    ix->batch->d_row_query.release();
     ix->batch->d_meta.release();
+    ix->batch->d_pstats.release();
     delete ix->batch;
     ix->batch = nullptr;
 }

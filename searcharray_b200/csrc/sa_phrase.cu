@@ -468,7 +468,7 @@ __global__ void bm25_dense_kernel(float *__restrict__ tf, const float *__restric
 static u64 padded(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
 
 // direction / speculation plan exactly as compute_phrase_freqs picks it (middle_out.py:154-168)
-static void plan_phrase(PhraseQuery &pq, const u32 *term_ids) {
+void sa_phrase_plan(PhraseQuery &pq, const u32 *term_ids) {
     const u32 n = pq.n_terms;
     u32 shortest = 0;
     for (u32 i = 1; i < n; i++) if (pq.len[i] < pq.len[shortest]) shortest = i;   // first minimum
@@ -501,7 +501,7 @@ static void step_order(const PhraseQuery &pq, std::vector<u32> &order) {
 
 // Runs phrase queries (already planned) into ix->dense; loops until the same-term speculation
 // of every query is confirmed.  lists may live in ix->d_words (off = absolute word offsets).
-static int run_phrase_queries(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
+int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
                               int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump) {
     const u32 Q = (u32)pqs.size();
     const u64 stride = padded(ix->n_docs);
@@ -576,6 +576,53 @@ static int run_phrase_queries(sa_index *ix, std::vector<PhraseQuery> &pqs, const
     return SA_ERR_ARG;
 }
 
+// Checks the same-term speculation of one finished query; on the first wrong guess (in step
+// order) flips it and returns false: the query must run again.
+bool sa_phrase_guess_ok(PhraseQuery &pq, const PhraseStats &st) {
+    std::vector<u32> order;
+    step_order(pq, order);
+    for (u32 s : order) {
+        bool actual = st.n_inner[s] > 0 && st.n_diff[s] == 0;
+        bool guess = (pq.same_guess >> s) & 1u;
+        if (actual != guess) {
+            pq.same_guess ^= 1u << s;
+            return false;
+        }
+    }
+    return true;
+}
+
+u64 sa_phrase_arena_words(const PhraseQuery &pq, u32 n_chunks) {
+    u64 sum = 0;
+    for (u32 t = 0; t < pq.n_terms; t++) sum += pq.len[t];
+    return 6 * (sum + 2ull * n_chunks);
+}
+
+// Asynchronous launch of already planned phrase queries living in device memory; dense rows,
+// stats and the arena counter must have been zeroed by the caller.
+int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_stats, u32 Q,
+                      float *dense_rows, u64 stride, u32 n_chunks, u64 *d_arena,
+                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p) {
+    PhraseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.words = ix->d_words;
+    a.doc_lens = ix->d_doc_lens;
+    a.n_docs = ix->n_docs;
+    a.doc_base = ix->doc_base;
+    a.queries = d_pqs;
+    a.stats = d_stats;
+    a.out = dense_rows;
+    a.out_stride = stride;
+    a.n_chunks = n_chunks;
+    a.docs_per_chunk = (ix->n_docs + n_chunks - 1) / n_chunks;
+    a.arena = d_arena;
+    a.arena_used = d_arena_used;
+    a.arena_cap = arena_words;
+    a.bm25 = p;
+    a.score = score;
+    return launch_phrase(ix, a, Q);
+}
+
 static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
                          int score, float idf, float avg_doc_len, float k1, float b,
                          uint64_t min_payload, uint64_t max_payload, float *out_host) {
@@ -616,11 +663,11 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
             pq.off[i] = ix->h_off[term_ids[i]];
             pq.len[i] = ix->h_len[term_ids[i]];
         }
-        plan_phrase(pq, term_ids);
+        sa_phrase_plan(pq, term_ids);
         PhraseDump nodump;
         memset(&nodump, 0, sizeof(nodump));
         // raw counts first when BM25 must touch every doc
-        if ((rc = run_phrase_queries(ix, pqs, ix->d_words, score && p.sparse_ok, p, 0, nodump))) return rc;
+        if ((rc = sa_phrase_run_sync(ix, pqs, ix->d_words, score && p.sparse_ok, p, 0, nodump))) return rc;
     } else {
         if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
         SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, stride * sizeof(float), ix->stream));
@@ -688,7 +735,7 @@ extern "C" int sa_op_bigram_freqs(const uint64_t *lhs, uint64_t n_lhs, const uin
             cudaMemsetAsync(dump.n_cont, 0, 2 * sizeof(u64), ix->stream);
             Bm25Params p;
             memset(&p, 0, sizeof(p));
-            rc = run_phrase_queries(ix, pqs, ix->d_words, 0, p, 1, dump);
+            rc = sa_phrase_run_sync(ix, pqs, ix->d_words, 0, p, 1, dump);
             if (!rc) {
                 u64 n[2];
                 cudaMemcpy(n, dump.n_cont, 2 * sizeof(u64), cudaMemcpyDeviceToHost);

@@ -53,3 +53,11 @@ struct PhraseArgs {
 };
 
 int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries);
+void sa_phrase_plan(PhraseQuery &pq, const u32 *term_ids);
+bool sa_phrase_guess_ok(PhraseQuery &pq, const PhraseStats &st);
+u64 sa_phrase_arena_words(const PhraseQuery &pq, u32 n_chunks);
+int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_stats, u32 Q,
+                      float *dense_rows, u64 stride, u32 n_chunks, u64 *d_arena,
+                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p);
+int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
+                       int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump);

@@ -55,7 +55,7 @@ __device__ __forceinline__ void radix_pick(const u32 *hist, u32 &rem, int &bin) 
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
+topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys, const u32 *__restrict__ out_index) {
     __shared__ u64 s_keys[SEL_SMEM_KEYS];
     __shared__ u32 s_hist[256];
     __shared__ u64 s_prefix;
@@ -170,7 +170,7 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys) {
     for (u32 i = threadIdx.x; i < k; i += blockDim.x) {
         u64 key = (i < n_valid) ? s_keys[i] : 0ull;
         if (key != 0ull) key -= doc_base;      // (~local) - base == ~(local + base)
-        out_keys[(u64)q * k + i] = key;
+        out_keys[(u64)(out_index ? out_index[q] : q) * k + i] = key;
     }
 }
 
@@ -195,10 +195,11 @@ topk_merge_kernel(const u64 *__restrict__ in, u32 world, u32 n_queries, u32 k, u
     for (u32 i = threadIdx.x; i < k; i += blockDim.x) out[(u64)q * k + i] = s_keys[i];
 }
 
-int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys) {
+int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys,
+                       const u32 *d_out_index) {
     if (n_queries == 0) return SA_OK;
     KernelTimer tm(ix, 1);
-    topk_select_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(t, doc_base, d_out_keys);
+    topk_select_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(t, doc_base, d_out_keys, d_out_index);
     SA_CUDA(cudaGetLastError());
     tm.stop();
     ix->stats.topk_kernel_launches++;

@@ -147,3 +147,32 @@ def test_random_corpus_vs_oracle():
         np.testing.assert_allclose(sg, sw, rtol=1e-5, atol=0)
         checked += int(want.sum() > 0)
     assert checked > 10
+
+
+def test_batch_topk_mixed_terms_and_phrases():
+    """sa_score_batch_topk with term and phrase queries interleaved, vs the oracle's full sort."""
+    from oracle import search as osearch
+    from searcharray_b200 import SearchArray
+    rng = np.random.default_rng(5)
+    vocab = [f"v{i}" for i in range(10)]
+    p = 1.0 / np.arange(1, 11)
+    p /= p.sum()
+    docs = [" ".join(rng.choice(vocab, size=int(rng.integers(1, 90)), p=p)) for _ in range(20_000)]
+    arr = SearchArray.index(docs)
+    host = arr.host
+    oidx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
+                               avg_doc_length=host.avg_doc_length)
+    tid = host.term_dict.term_to_ids
+    queries = ["v0", ["v0", "v1"], "v7", ["v1", "v0", "v2"], ["v3", "v3"], "nope", ["v0", "nope"],
+               ["v2", "v1", "v0", "v3"], "v9", ["v0", "v0", "v0"], ["v5", "v1"]]
+    for k in (3, 10):
+        got_docs, got_scores = arr.search_topk(queries, k=k)
+        for qi, q in enumerate(queries):
+            toks = [q] if isinstance(q, str) else q
+            ids = [tid.get(t) for t in toks]
+            s = oidx.score(ids[0] if len(ids) == 1 else ids)
+            order = np.lexsort((np.arange(len(s)), -s.astype(np.float64)))[:k]
+            order = order[s[order] > 0]
+            assert np.array_equal(got_docs[qi][:len(order)], order.astype(np.uint32)), (q, k)
+            np.testing.assert_allclose(got_scores[qi][:len(order)], s[order], rtol=1e-5, atol=0)
+            assert np.all(got_docs[qi][len(order):] == 0xFFFFFFFF)
