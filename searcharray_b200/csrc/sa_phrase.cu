@@ -28,6 +28,8 @@
 #include "sa_phrase.cuh"
 #include "sa_term.cuh"
 
+int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop, u32 *n_undefined);
+
 #define PT SA_PHRASE_THREADS
 
 struct Elem {
@@ -629,7 +631,6 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
     SA_CHECK(ix && term_ids && out_host, "NULL argument");
     SA_CHECK(n_terms >= 2, "Must have at least two terms");
     SA_CHECK(n_terms <= SA_MAX_PHRASE_TERMS, "phrases longer than %d terms are not supported", SA_MAX_PHRASE_TERMS);
-    SA_CHECK(slop == 0, "slop > 0 is not implemented yet");
     SA_CHECK(min_payload == 0 && max_payload == SA_ALL_BITS, "min_posn/max_posn on phrases is not implemented yet");
     SA_CHECK(ix->n_rows == 0, "phrase search on a sliced array is not implemented yet");
     std::lock_guard<std::mutex> g(ix->mu);
@@ -653,7 +654,12 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
                    !std::signbit(idf)) ? 1 : 0;
     const u64 stride = padded(ix->n_docs);
     int rc;
-    if (!missing) {
+    bool raw_counts = false;          // dense row holds raw phrase freqs that still need BM25
+    if (!missing && slop > 0) {
+        // span search (phrase/spans.py + roaringish/spans.pyx): raw counts, BM25 afterwards
+        if ((rc = sa_span_run(ix, term_ids, n_terms, slop, nullptr))) return rc;
+        raw_counts = score != 0;
+    } else if (!missing) {
         std::vector<PhraseQuery> pqs(1);
         PhraseQuery &pq = pqs[0];
         memset(&pq, 0, sizeof(pq));
@@ -668,11 +674,13 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
         memset(&nodump, 0, sizeof(nodump));
         // raw counts first when BM25 must touch every doc
         if ((rc = sa_phrase_run_sync(ix, pqs, ix->d_words, score && p.sparse_ok, p, 0, nodump))) return rc;
+        raw_counts = score && !p.sparse_ok;
     } else {
         if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
         SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, stride * sizeof(float), ix->stream));
+        raw_counts = score && !p.sparse_ok;
     }
-    if (score && !p.sparse_ok) {
+    if (raw_counts) {     // bm25.pyx:20-25 over every doc (tf == 0 scores +0.0 for ordinary parameters)
         unsigned blocks = (unsigned)((ix->n_docs + 255) / 256);
         bm25_dense_kernel<<<blocks, 256, 0, ix->stream>>>(ix->dense.as<float>(), ix->d_doc_lens, ix->n_docs, p);
         SA_CUDA(cudaGetLastError());
