@@ -169,27 +169,179 @@ span_candidates_kernel(const SpanArgs a) {
             __syncthreads();
         }
     }
-    // doc groups of every sliced list
-    for (u32 t = 0; t < n; t++) {
-        const u32 cnt = min(s_count[t], (u32)sq.s_cap[t]);
+    if (tid < n) a.counts[q].n_sliced[tid] = min(s_count[tid], (u32)sq.s_cap[tid]);
+}
+
+// doc groups of every sliced list (runs after either candidate kernel)
+__global__ void __launch_bounds__(CAND_THREADS)
+span_groups_build_kernel(const SpanArgs a) {
+    __shared__ u32 s_warp[CAND_THREADS / 32];
+    __shared__ u32 s_groups;
+    const u32 q = blockIdx.x;
+    const SpanQuery &sq = a.queries[q];
+    const unsigned tid = threadIdx.x;
+    for (u32 t = 0; t < sq.n_terms; t++) {
+        const u32 cnt = a.counts[q].n_sliced[t];
         const u64 *sl = a.word_arena + sq.s_off[t];
+        if (tid == 0) s_groups = 0;
+        __syncthreads();
         for (u32 base = 0; base < cnt; base += CAND_THREADS) {
             const u32 i = base + tid;
             bool start = false;
             if (i < cnt) start = (i == 0) || ((sl[i] >> SA_KEY_SHIFT) != (sl[i - 1] >> SA_KEY_SHIFT));
             u32 total;
             u32 off = block_scan_excl(start ? 1u : 0u, s_warp, total);
-            const u32 g0 = s_groups[t];
+            const u32 g0 = s_groups;
             if (start) a.group_arena[sq.g_off[t] + g0 + off] = i;
             __syncthreads();
-            if (tid == 0) s_groups[t] = g0 + total;
+            if (tid == 0) s_groups = g0 + total;
             __syncthreads();
         }
         if (tid == 0) {
-            a.group_arena[sq.g_off[t] + s_groups[t]] = cnt;          // sentinel: end of the last group
-            a.counts[q].n_sliced[t] = cnt;
-            a.counts[q].n_groups[t] = s_groups[t];
+            a.group_arena[sq.g_off[t] + s_groups] = cnt;          // sentinel: end of the last group
+            a.counts[q].n_groups[t] = s_groups;
         }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------- phase 1, literal (rare) variant
+// When every term has a word at header 0 (doc 0, block 0) the reference's `last_lhs_headers - 1
+// block` (spans.py:104) underflows on its first element; the merges and the galloping slice that
+// follow then run on a list that is no longer sorted, and WHICH candidate words survive depends on
+// the exact pointer walk.  That is deterministic, so it is replayed literally -- one thread, the
+// reference's own sequence of galloping intersects / adjacents / merges (the restatement follows
+// searcharray/roaringish/intersect.pyx:32-190 and merge.pyx:54-134).  Only this corner takes it.
+struct U64Buf { u64 *p; u64 n; };
+
+#define DEV_GALLOP(ptr, end, cond)                    \
+    do {                                              \
+        u64 stride_ = 1;                              \
+        while ((ptr) < (end) && (cond)) {             \
+            (ptr) += stride_;                         \
+            stride_ <<= 1;                            \
+        }                                             \
+        (ptr) -= (stride_ >> 1);                      \
+    } while (0)
+
+__device__ u64 dev_intersect_drop(const u64 *lhs, u64 nl, const u64 *rhs, u64 nr, u64 mask, u64 *li, u64 *ri) {
+    const u64 *l = lhs, *r = rhs, *le = lhs + nl, *re = rhs + nr;
+    u64 m = 0, last = ~0ull;
+    while (l < le && r < re) {
+        DEV_GALLOP(l, le, (*l & mask) < (*r & mask));
+        DEV_GALLOP(r, re, (*r & mask) < (*l & mask));
+        const u64 x = *l & mask, y = *r & mask;
+        if (x < y) l++;
+        else if (y < x) r++;
+        else {
+            if ((last & mask) != x) { li[m] = (u64)(l - lhs); if (ri) ri[m] = (u64)(r - rhs); last = *l; m++; }
+            l++; r++;
+        }
+    }
+    return m;
+}
+
+__device__ u64 dev_adjacent(const u64 *lhs, u64 nl, const u64 *rhs, u64 nr, u64 mask, u64 *li, u64 *ri) {
+    const u64 delta = mask & (~mask + 1);
+    const u64 *l = lhs, *r = rhs, *le = lhs + nl, *re = rhs + nr;
+    u64 m = 0, last = ~0ull;
+    while (r < re && (*r & mask) == 0) r++;
+    while (l < le && r < re) {
+        DEV_GALLOP(l, le, (*l & mask) < ((*r & mask) - delta));
+        DEV_GALLOP(r, re, ((*r & mask) - delta) < (*l & mask));
+        const u64 x = *l & mask, y = (*r & mask) - delta;
+        if (x < y) l++;
+        else if (y < x) r++;
+        else {
+            if ((last & mask) != x) { li[m] = (u64)(l - lhs); ri[m] = (u64)(r - rhs); last = *l; m++; }
+            l++; r++;
+        }
+    }
+    return m;
+}
+
+__device__ u64 dev_merge(const u64 *lhs, u64 nl, const u64 *rhs, u64 nr, bool drop, u64 *out) {
+    u64 i = 0, j = 0, m = 0;
+    while (i < nl && j < nr) {
+        if (lhs[i] < rhs[j]) out[m++] = lhs[i++];
+        else if (rhs[j] < lhs[i]) out[m++] = rhs[j++];
+        else { out[m++] = lhs[i]; if (!drop) out[m++] = rhs[j]; i++; j++; }
+    }
+    while (j < nr) out[m++] = rhs[j++];
+    while (i < nl) out[m++] = lhs[i++];
+    return m;
+}
+
+// all rhs elements whose value occurs in lhs, found the way _gallop_intersect_keep walks
+__device__ u64 dev_intersect_keep_rhs(const u64 *lhs, u64 nl, const u64 *rhs, u64 nr, u64 hdr_mask_rhs, u64 *r_out) {
+    // lhs: header values (possibly unsorted here!), rhs: words compared by (word & hdr_mask_rhs)
+    const u64 *l = lhs, *r = rhs, *le = lhs + nl, *re = rhs + nr;
+    u64 m = 0;
+    while (l < le && r < re) {
+        DEV_GALLOP(l, le, *l < (*r & hdr_mask_rhs));
+        DEV_GALLOP(r, re, (*r & hdr_mask_rhs) < *l);
+        const u64 x = *l, y = *r & hdr_mask_rhs;
+        if (x < y) l++;
+        else if (y < x) r++;
+        else {
+            while (l < le && *l == x) l++;
+            while (r < re && (*r & hdr_mask_rhs) == x) { r_out[m++] = *r; r++; }
+        }
+    }
+    return m;
+}
+
+__global__ void span_candidates_literal_kernel(const SpanArgs a, u64 *scratch, u64 cap3 /* 3*|A| + 8 */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const SpanQuery &sq = a.queries[0];
+    const u32 n = sq.n_terms;
+    const u64 M = SA_HDR_MASK;
+    u64 *lh = scratch, *rh = lh + cap3, *tmp = rh + cap3, *tmp2 = tmp + cap3;
+    u64 *last_l = tmp2 + cap3, *last_r = last_l + cap3;
+    u64 *i0 = last_r + cap3, *i1 = i0 + cap3, *allh = i1 + cap3, *allh2 = allh + 4 * cap3;
+    u64 n_ll = 0, n_lr = 0;
+    const u64 *curr = a.words + sq.off[0];
+    const u64 nc = sq.len[0];
+    for (u32 k = 1; k < n; k++) {
+        const u64 *nxt = a.words + sq.off[k];
+        const u64 nn = sq.len[k];
+        u64 m = dev_intersect_drop(curr, nc, nxt, nn, M, i0, nullptr);
+        for (u64 j = 0; j < m; j++) tmp[j] = curr[i0[j]] & M;                     // int_headers
+        u64 ma = dev_adjacent(curr, nc, nxt, nn, M, i0, i1);                      // curr_to_right, next_to_left
+        for (u64 j = 0; j < ma; j++) tmp2[j] = nxt[i1[j]];
+        u64 n_lh = dev_merge(tmp, m, tmp2, ma, false, lh);
+        for (u64 j = 0; j < ma; j++) tmp2[j] = curr[i0[j]];
+        u64 n_rh = dev_merge(tmp, m, tmp2, ma, false, rh);
+        u64 mb = dev_adjacent(nxt, nn, curr, nc, M, i0, i1);                      // next_to_right, curr_to_left
+        for (u64 j = 0; j < mb; j++) tmp2[j] = curr[i1[j]];
+        n_lh = dev_merge(lh, n_lh, tmp2, mb, false, tmp);
+        for (u64 j = 0; j < n_lh; j++) lh[j] = tmp[j];
+        for (u64 j = 0; j < mb; j++) tmp2[j] = nxt[i0[j]];
+        n_rh = dev_merge(rh, n_rh, tmp2, mb, false, tmp);
+        for (u64 j = 0; j < n_rh; j++) rh[j] = tmp[j];
+        if (k > 1) {
+            u64 ml = dev_intersect_drop(last_l, n_ll, lh, n_lh, M, i0, nullptr);
+            for (u64 j = 0; j < ml; j++) last_l[j] = last_l[i0[j]];              // ascending: in place is safe
+            n_ll = ml;
+            u64 mr = dev_intersect_drop(last_r, n_lr, rh, n_rh, M, i0, nullptr);
+            for (u64 j = 0; j < mr; j++) last_r[j] = last_r[i0[j]];
+            n_lr = mr;
+        } else {
+            for (u64 j = 0; j < n_lh; j++) last_l[j] = lh[j];
+            for (u64 j = 0; j < n_rh; j++) last_r[j] = rh[j];
+            n_ll = n_lh;
+            n_lr = n_rh;
+        }
+    }
+    for (u64 j = 0; j < n_lr; j++) tmp[j] = last_r[j] + SA_ONE_BLOCK;             // to_rhs
+    for (u64 j = 0; j < n_ll; j++) tmp2[j] = last_l[j] - SA_ONE_BLOCK;            // to_lhs (may underflow)
+    u64 na = dev_merge(tmp, n_lr, tmp2, n_ll, true, allh);
+    na = dev_merge(last_l, n_ll, allh, na, true, allh2);
+    na = dev_merge(last_r, n_lr, allh2, na, true, allh);
+    for (u64 j = 0; j < na; j++) allh[j] &= M;
+    for (u32 t = 0; t < n; t++) {
+        u64 m = dev_intersect_keep_rhs(allh, na, a.words + sq.off[t], sq.len[t], M, a.word_arena + sq.s_off[t]);
+        a.counts[0].n_sliced[t] = (u32)m;
     }
 }
 
@@ -422,7 +574,27 @@ int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32
     a.doc_base = ix->doc_base;
     {
         KernelTimer t(ix, 2);
-        span_candidates_kernel<<<1, CAND_THREADS, 0, ix->stream>>>(a);
+        // the reference's header-0 underflow corner (see span_candidates_literal_kernel)
+        bool literal = true;
+        for (u32 t = 0; t < n_terms; t++) {
+            u64 first = 0;
+            SA_CUDA(cudaMemcpyAsync(&first, ix->d_words + sq.off[t], sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+            SA_CUDA(cudaStreamSynchronize(ix->stream));
+            if ((first & SA_HDR_MASK) != 0) { literal = false; break; }
+        }
+        if (literal) {
+            const u64 cap3 = 3 * sq.len[0] + 3 * shortest_len + 16;
+            DevBuf lit;
+            if ((rc = lit.reserve((9 * cap3 + 8 * cap3) * sizeof(u64)))) return rc;
+            span_candidates_literal_kernel<<<1, 1, 0, ix->stream>>>(a, lit.as<u64>(), cap3);
+            SA_CUDA(cudaGetLastError());
+            SA_CUDA(cudaStreamSynchronize(ix->stream));
+            lit.release();
+        } else {
+            span_candidates_kernel<<<1, CAND_THREADS, 0, ix->stream>>>(a);
+            SA_CUDA(cudaGetLastError());
+        }
+        span_groups_build_kernel<<<1, CAND_THREADS, 0, ix->stream>>>(a);
         SA_CUDA(cudaGetLastError());
         SA_CUDA(cudaFuncSetAttribute(span_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(SPAN_WARPS * sizeof(WarpSpans))));
@@ -430,8 +602,8 @@ int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32
         span_groups_kernel<<<blocks, SPAN_WARPS * 32, SPAN_WARPS * sizeof(WarpSpans), ix->stream>>>(a, 1);
         SA_CUDA(cudaGetLastError());
         t.stop();
-        ix->stats.phrase_kernel_launches += 2;
-        ix->stats.total_launches += 2;
+        ix->stats.phrase_kernel_launches += 3;
+        ix->stats.total_launches += 3;
     }
     SpanCounts h;
     SA_CUDA(cudaMemcpyAsync(&h, ix->cand_meta.p, sizeof(h), cudaMemcpyDeviceToHost, ix->stream));
