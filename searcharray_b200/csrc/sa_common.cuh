@@ -120,7 +120,8 @@ struct sa_index {
     std::vector<u32> h_df;
 
     // sliced-array filter (FilteredPosns semantics)
-    u64 n_rows = 0;                  // 0 => no filter
+    u64 n_rows = 0;                  // number of selected rows
+    bool rows_active = false;        // a row filter is installed (n_rows may be 0)
     u64 *d_rows = nullptr;           // sorted local doc indices
     unsigned char *d_row_mask = nullptr;  // [n_docs] 1 if doc selected
 
@@ -140,6 +141,7 @@ struct sa_index {
     DevBuf cand_meta;    // per-query counters / thresholds
     DevBuf topk_out;     // per-query (doc, score) results
     DevBuf phrase_scratch;
+    DevBuf filt;         // filtered (sliced / position-filtered) copies of posting lists
     DevBuf misc;
     void *h_pinned = nullptr;   // pinned staging
     size_t h_pinned_cap = 0;

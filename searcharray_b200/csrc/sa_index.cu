@@ -246,6 +246,7 @@ extern "C" int sa_index_destroy(sa_index *ix) {
     ix->cand_meta.release();
     ix->topk_out.release();
     ix->phrase_scratch.release();
+    ix->filt.release();
     ix->misc.release();
     ix->gather.release();
     sa_free_batch(ix);
@@ -323,6 +324,10 @@ static Bm25Params make_bm25(const sa_index *ix, float idf, float avg_doc_len, fl
 
 static u64 padded_docs(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
 
+int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bool use_rows,
+                    u64 pay_lo, u64 pay_hi, bool use_payload, std::vector<u64> &offs, std::vector<u64> &lens);
+int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
+
 static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Params &p,
                        u64 min_payload, u64 max_payload, float *out_host) {
     SA_CHECK(ix && out_host, "NULL argument");
@@ -330,6 +335,8 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
     std::lock_guard<std::mutex> g(ix->mu);
     SA_CUDA(cudaSetDevice(ix->device));
     if (ix->n_docs == 0) return SA_OK;
+    const bool rows = ix->rows_active;
+    SA_CHECK(!(rows && mode == TERM_MODE_SCORE), "score on a sliced array: call termfreqs + bm25 (the Python layer does)");
     const u64 stride = padded_docs(ix->n_docs);
     int rc = ix->dense.reserve(stride * sizeof(float));
     if (rc) return rc;
@@ -341,10 +348,22 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
     tq.n_words = term_id == SA_NO_TERM ? 0 : ix->h_len[term_id];
     tq.dir_off = term_id == SA_NO_TERM ? SA_NO_DIR : ix->h_dir_off[term_id];
     tq.idf = p.idf;
+    const u64 *words = ix->d_words;
+    bool filter = !(min_payload == 0 && max_payload == SA_ALL_BITS);
+    if (rows && term_id != SA_NO_TERM) {
+        // sliced array: run on the materialised FilteredPosns list (rows and block filter applied)
+        std::vector<u64> offs, lens;
+        if ((rc = sa_filter_terms(ix, &term_id, 1, true, min_payload, max_payload, filter, offs, lens))) return rc;
+        words = ix->filt.as<u64>();
+        tq.word_off = offs[0];
+        tq.n_words = lens[0];
+        tq.dir_off = SA_NO_DIR;
+        filter = false;
+    }
     SA_CUDA(cudaMemcpyAsync(ix->queries.p, &tq, sizeof(tq), cudaMemcpyHostToDevice, ix->stream));
     TermBatchArgs a;
     memset(&a, 0, sizeof(a));
-    a.words = ix->d_words;
+    a.words = words;
     a.doc_lens = ix->d_doc_lens;
     a.n_docs = ix->n_docs;
     a.doc_base = ix->doc_base;
@@ -354,11 +373,12 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
     a.bm25 = p;
     a.min_payload = min_payload;
     a.max_payload = max_payload;
-    a.filter = !(min_payload == 0 && max_payload == SA_ALL_BITS);
+    a.filter = filter;
     a.mode = mode;
     a.topk.k = 0;
     rc = launch_term_batch(ix, a, 1);
     if (rc) return rc;
+    if (rows) return sa_gather_rows(ix, ix->dense.as<float>(), out_host);
     SA_CUDA(cudaMemcpyAsync(out_host, ix->dense.p, ix->n_docs * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
     return SA_OK;

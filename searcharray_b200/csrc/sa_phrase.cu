@@ -28,7 +28,11 @@
 #include "sa_phrase.cuh"
 #include "sa_term.cuh"
 
-int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop, u32 *n_undefined);
+int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, uint32_t n_terms, uint32_t slop,
+                u32 *n_undefined);
+int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bool use_rows,
+                    u64 pay_lo, u64 pay_hi, bool use_payload, std::vector<u64> &offs, std::vector<u64> &lens);
+int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
 
 #define PT SA_PHRASE_THREADS
 
@@ -631,8 +635,6 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
     SA_CHECK(ix && term_ids && out_host, "NULL argument");
     SA_CHECK(n_terms >= 2, "Must have at least two terms");
     SA_CHECK(n_terms <= SA_MAX_PHRASE_TERMS, "phrases longer than %d terms are not supported", SA_MAX_PHRASE_TERMS);
-    SA_CHECK(min_payload == 0 && max_payload == SA_ALL_BITS, "min_posn/max_posn on phrases is not implemented yet");
-    SA_CHECK(ix->n_rows == 0, "phrase search on a sliced array is not implemented yet");
     std::lock_guard<std::mutex> g(ix->mu);
     SA_CUDA(cudaSetDevice(ix->device));
     if (ix->n_docs == 0) return SA_OK;
@@ -644,8 +646,8 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
     if (missing || (score && avg_doc_len == 0.0f)) {
         // unknown term inside a phrase -> zeros (postings.py:705-708); with tf == 0 everywhere BM25
         // still runs over all docs in the reference, which only matters for exotic parameters
-        memset(out_host, 0, ix->n_docs * sizeof(float));
-        if (!(score && avg_doc_len != 0.0f)) return SA_OK;
+        memset(out_host, 0, (ix->rows_active ? ix->n_rows : ix->n_docs) * sizeof(float));
+        if (!(score && avg_doc_len != 0.0f) || ix->rows_active) return SA_OK;
     }
     Bm25Params p;
     p.idf = idf; p.avg_doc_len = avg_doc_len; p.k1 = k1; p.b = b; p.one_minus_b = 1 - b;
@@ -655,9 +657,22 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
     const u64 stride = padded(ix->n_docs);
     int rc;
     bool raw_counts = false;          // dense row holds raw phrase freqs that still need BM25
+    const bool use_payload = !(min_payload == 0 && max_payload == SA_ALL_BITS);
+    const bool rows = ix->rows_active;
+    SA_CHECK(!(rows && score), "score on a sliced array: call termfreqs + bm25 (the Python layer does)");
+    // term lists: the index's own, or filtered copies (sliced array / min-max posn), which is what
+    // the reference runs on (middle_out.py:427-437: encoder.slice per term, then the same algorithm)
+    std::vector<u64> offs(n_terms), lens(n_terms);
+    const u64 *d_lists = ix->d_words;
+    if (!missing && (rows || use_payload)) {
+        if ((rc = sa_filter_terms(ix, term_ids, n_terms, rows, min_payload, max_payload, use_payload, offs, lens))) return rc;
+        d_lists = ix->filt.as<u64>();
+    } else if (!missing) {
+        for (u32 i = 0; i < n_terms; i++) { offs[i] = ix->h_off[term_ids[i]]; lens[i] = ix->h_len[term_ids[i]]; }
+    }
     if (!missing && slop > 0) {
         // span search (phrase/spans.py + roaringish/spans.pyx): raw counts, BM25 afterwards
-        if ((rc = sa_span_run(ix, term_ids, n_terms, slop, nullptr))) return rc;
+        if ((rc = sa_span_run(ix, d_lists, offs.data(), lens.data(), n_terms, slop, nullptr))) return rc;
         raw_counts = score != 0;
     } else if (!missing) {
         std::vector<PhraseQuery> pqs(1);
@@ -666,14 +681,14 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
         pq.n_terms = n_terms;
         pq.idf = idf;
         for (u32 i = 0; i < n_terms; i++) {
-            pq.off[i] = ix->h_off[term_ids[i]];
-            pq.len[i] = ix->h_len[term_ids[i]];
+            pq.off[i] = offs[i];
+            pq.len[i] = lens[i];
         }
         sa_phrase_plan(pq, term_ids);
         PhraseDump nodump;
         memset(&nodump, 0, sizeof(nodump));
         // raw counts first when BM25 must touch every doc
-        if ((rc = sa_phrase_run_sync(ix, pqs, ix->d_words, score && p.sparse_ok, p, 0, nodump))) return rc;
+        if ((rc = sa_phrase_run_sync(ix, pqs, d_lists, score && p.sparse_ok, p, 0, nodump))) return rc;
         raw_counts = score && !p.sparse_ok;
     } else {
         if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
@@ -686,6 +701,7 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
         SA_CUDA(cudaGetLastError());
         ix->stats.total_launches++;
     }
+    if (rows) return sa_gather_rows(ix, ix->dense.as<float>(), out_host);
     SA_CUDA(cudaMemcpyAsync(out_host, ix->dense.p, ix->n_docs * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
     return SA_OK;
@@ -812,15 +828,3 @@ extern "C" int sa_op_bm25_score(float *tf_inout, const float *doc_lens, uint64_t
     return SA_OK;
 }
 
-// ------------------------------------------------------ sliced arrays (not implemented yet)
-extern "C" int sa_index_set_rows(sa_index *ix, const uint64_t *rows, uint64_t n_rows) {
-    SA_CHECK(ix, "index is NULL");
-    if (rows == nullptr && n_rows == 0) { ix->n_rows = 0; return SA_OK; }
-    sa_set_error("sa_index_set_rows: sliced arrays are not implemented yet");
-    return SA_ERR_ARG;
-}
-
-extern "C" int sa_docfreq_rows(sa_index *, uint32_t, uint64_t *) {
-    sa_set_error("sa_docfreq_rows: sliced arrays are not implemented yet");
-    return SA_ERR_ARG;
-}

@@ -533,7 +533,8 @@ span_groups_kernel(const SpanArgs a, u32 n_queries) {
 static u64 padded_stride(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
 
 // Span search of one query into ix->dense row 0 (raw counts).  Caller holds ix->mu.
-int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop, u32 *n_undefined) {
+int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, uint32_t n_terms, uint32_t slop,
+                u32 *n_undefined) {
     const u64 stride = padded_stride(ix->n_docs);
     int rc;
     if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
@@ -544,8 +545,8 @@ int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32
     sq.slop = slop;
     u64 shortest_len = ~0ull;
     for (u32 t = 0; t < n_terms; t++) {
-        sq.off[t] = ix->h_off[term_ids[t]];
-        sq.len[t] = ix->h_len[term_ids[t]];
+        sq.off[t] = offs[t];
+        sq.len[t] = lens[t];
         if (sq.len[t] < shortest_len) { shortest_len = sq.len[t]; sq.shortest = t; }
     }
     u64 words_total = 0, groups_total = 0;
@@ -563,7 +564,7 @@ int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32
     SA_CUDA(cudaMemcpyAsync(ix->queries.p, &sq, sizeof(sq), cudaMemcpyHostToDevice, ix->stream));
     SA_CUDA(cudaMemsetAsync(ix->cand_meta.p, 0, sizeof(SpanCounts), ix->stream));
     SpanArgs a;
-    a.words = ix->d_words;
+    a.words = d_lists;
     a.queries = ix->queries.as<SpanQuery>();
     a.counts = ix->cand_meta.as<SpanCounts>();
     a.word_arena = ix->phrase_scratch.as<u64>();
@@ -578,7 +579,8 @@ int sa_span_run(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32
         bool literal = true;
         for (u32 t = 0; t < n_terms; t++) {
             u64 first = 0;
-            SA_CUDA(cudaMemcpyAsync(&first, ix->d_words + sq.off[t], sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+            if (sq.len[t] == 0) { literal = false; break; }
+            SA_CUDA(cudaMemcpyAsync(&first, d_lists + sq.off[t], sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
             SA_CUDA(cudaStreamSynchronize(ix->stream));
             if ((first & SA_HDR_MASK) != 0) { literal = false; break; }
         }

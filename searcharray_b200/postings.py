@@ -182,6 +182,7 @@ class SearchArray(ExtensionArray):
         self.avg_doc_length = host.avg_doc_length
         self.corpus_size = host.n_docs
         self.rows = None                 # sliced view: local doc ids (postings.py:344-358)
+        self._bm25_doc_lens = None
         self._shared = {"dev": None, "lock": threading.Lock()}   # shared by views/copies
 
     @classmethod
@@ -265,6 +266,15 @@ class SearchArray(ExtensionArray):
         view = SearchArray.__new__(SearchArray)
         view.__dict__.update(self.__dict__)
         view.rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        # Reference quirk: `arr.doc_lens = self.doc_lens[key]` (postings.py:353) is a STRIDED VIEW
+        # for a stepped slice and bm25_score walks it contiguously (bm25.pyx:34-41), i.e. BM25 on
+        # arr[a::s] sees the parent's doc_lens[a], [a+1], ...  Reproduced for parity.
+        view._bm25_doc_lens = None
+        if isinstance(key, slice) and key.step not in (None, 1) and len(rows):
+            parent = self.doclengths()
+            first = int(np.arange(len(parent))[key][0])
+            if first + len(rows) <= len(parent):
+                view._bm25_doc_lens = np.ascontiguousarray(parent[first:first + len(rows)])
         return view
 
     def take(self, indices, allow_fill=False, fill_value=None):
@@ -382,6 +392,18 @@ class SearchArray(ExtensionArray):
             tfs = self.termfreqs(token, min_posn=min_posn, max_posn=max_posn, slop=slop)
             return similarity(tfs, all_dfs, self.doclengths(), self.avg_doc_length, self.corpus_size)
         lo, hi = self._payload_bounds(min_posn, max_posn)
+        if self.rows is not None:
+            # sliced array: tf on the filtered postings (FilteredPosns), then BM25 over the slice's
+            # rows with the slice's doc lengths -- both on the GPU (reference postings.py:674-680)
+            from . import ops
+            tfs = self.termfreqs(token, min_posn=min_posn, max_posn=max_posn, slop=slop)
+            if self.avg_doc_length == 0:
+                return np.zeros_like(tfs)
+            dl = getattr(self, "_bm25_doc_lens", None)
+            if dl is None:
+                dl = np.ascontiguousarray(self.doclengths())
+            idf = compute_idf(self.corpus_size, all_dfs)
+            return ops.bm25_score(tfs, dl, self.avg_doc_length, idf, similarity.k1, similarity.b, device=self.device)
         out = _pool.empty_f32(len(self))
         if self.avg_doc_length == 0:
             out[:] = 0
