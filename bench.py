@@ -408,6 +408,47 @@ def bench_ours(args, rank, world):
                   "min_list_words_mean": float(np.mean(np.min(Wp, axis=1))),
                   "repairs": int(p_redo),
                   "matches_in_top1": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF))}
+        # slop = 2 (BASELINE configs[3]) goes through the per-query C-ABI call: span search is
+        # latency/branch bound (informational, no roofline expectation)
+        if rank == 0 and world == 1 and args.slop_queries > 0:
+            from searcharray_b200.postings import _pool
+            out = _pool.empty_f32(host.n_docs)
+            ns = min(args.slop_queries, PQ)
+            _lib.check(L.sa_set_profiling(h, 1))
+            _lib.check(L.sa_stats_reset(h))
+            t0 = time.perf_counter()
+            matched = 0
+            for i in range(ns):
+                tids = np.ascontiguousarray(p_terms[4 * i:4 * i + 4])
+                _lib.check(L.sa_score_phrase(h, _lib.p_u32(tids), 4, 2, float(p_idf[i]), float(avgdl), K1, B, 0,
+                                             _lib.ALL_BITS, _lib.p_f32(out)))
+                matched += int(np.count_nonzero(out))
+            dt = time.perf_counter() - t0
+            _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
+            _lib.check(L.sa_set_profiling(h, 0))
+            phrase["slop2"] = {"workload": "4-term phrase, slop 2 (BASELINE configs[3]), sa_score_phrase per query, "
+                                           "dense float32[N] to the host", "queries": ns,
+                               "e2e": {"value": ns / dt, "unit": "queries/s"},
+                               "kernel_ms_per_query": stats.phrase_kernel_ms / ns,
+                               "mean_matching_docs": matched / ns}
+        # CPU side of the phrase workload: the oracle port, a few queries (each is 50-500 ms)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import search as osearch
+            oidx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
+                                       avg_doc_length=avgdl, corpus_size=args.docs, cache=True)
+            nsamp = min(8, PQ)
+            t0 = time.perf_counter()
+            for i in range(nsamp):
+                oidx.score([int(x) for x in p_terms[4 * i:4 * i + 4]], k1=K1, b=B)
+            dt0 = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            nslop = min(2, PQ)
+            for i in range(nslop):
+                oidx.score([int(x) for x in p_terms[4 * i:4 * i + 4]], k1=K1, b=B, slop=2)
+            dt2 = time.perf_counter() - t0
+            phrase["cpu_baseline"] = {"kind": "port", "cores": 1, "slop0_queries_per_s": nsamp / dt0,
+                                      "slop2_queries_per_s": nslop / dt2,
+                                      "sample": f"{nsamp} slop-0 and {nslop} slop-2 queries of the step, one thread"}
         upload()          # restore the term batch for the sections below
 
     # ---- e2e_dense: the literal .score() drop-in, dense float32[N] to the host per query
@@ -507,6 +548,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phrase-queries", type=int, default=256)
+    ap.add_argument("--slop-queries", type=int, default=16)
     ap.add_argument("--verify", type=int, default=0,
                     help="rank 0 re-generates the FULL corpus and checks this many queries' global top-k "
                          "against the CPU oracle (parity of the sharded / all-gathered path)")
