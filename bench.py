@@ -416,14 +416,14 @@ def bench_ours(args, rank, world):
             ns = min(args.slop_queries, PQ)
             _lib.check(L.sa_set_profiling(h, 1))
             _lib.check(L.sa_stats_reset(h))
-            t0 = time.perf_counter()
-            matched = 0
+            matched, dt = 0, 0.0
             for i in range(ns):
                 tids = np.ascontiguousarray(p_terms[4 * i:4 * i + 4])
+                t0 = time.perf_counter()
                 _lib.check(L.sa_score_phrase(h, _lib.p_u32(tids), 4, 2, float(p_idf[i]), float(avgdl), K1, B, 0,
                                              _lib.ALL_BITS, _lib.p_f32(out)))
+                dt += time.perf_counter() - t0
                 matched += int(np.count_nonzero(out))
-            dt = time.perf_counter() - t0
             _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
             _lib.check(L.sa_set_profiling(h, 0))
             phrase["slop2"] = {"workload": "4-term phrase, slop 2 (BASELINE configs[3]), sa_score_phrase per query, "
