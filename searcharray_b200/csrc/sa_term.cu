@@ -91,16 +91,12 @@ term_tile_kernel(const TermBatchArgs a) {
     const u32 tile_doc0 = tile * SA_TILE_DOCS;                       // local doc index
     const u32 tile_doc0_abs = (u32)a.doc_base + tile_doc0;           // as stored in the words
 
-    // 1. zero the tile; posting slice [lo, hi) of this tile
-#pragma unroll
-    for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
-        reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // 1. posting slice [lo, hi) of this tile
     u32 lo, hi;
     if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
         const u32 *dir = a.tile_dir + tq.dir_off + tile;
         lo = __ldg(dir);
         hi = __ldg(dir + 1);
-        __syncthreads();
     } else {
         if (warp < 2) {
             u64 key = (u64)tile_doc0_abs + (warp ? SA_TILE_DOCS : 0);
@@ -111,6 +107,95 @@ term_tile_kernel(const TermBatchArgs a) {
         lo = s_range[0];
         hi = s_range[1];
     }
+    const u32 k = a.topk.k;
+    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
+    constexpr u32 OWN = 30;
+    constexpr u32 WIN = (SA_TERM_THREADS / 32) * OWN;                  // words per CTA pass (240)
+
+    // 1b. SPARSE TILE (at most one window of words): no shared-memory tile at all.  The zeros go
+    //     straight to HBM at the start of the CTA -- the dominant 4N write is then independent of
+    //     the dir -> words -> norm load chain -- and the few scores are stored over them afterwards
+    //     (they merge with the zero lines in L2).  Each thread holds at most one score in a register.
+    if (!ALL_DOCS && hi - lo <= WIN) {
+#pragma unroll
+        for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++)
+            __stcs(out4 + tid + jj * SA_TERM_THREADS, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (k && tid == 0) { s_ncand = 0; s_tile_max = 0; }
+        __syncthreads();                       // zero stores are ordered before the score stores below
+        float v = 0.0f;
+        u32 my_rel = 0;
+        if (hi > lo) {
+            const u32 i = lo + warp * OWN + lane;
+            const u64 w = (i < n_words && i < hi + 2) ? __ldg(words + i) : ~0ull;
+            const u32 rel = (u32)(w >> SA_KEY_SHIFT) - tile_doc0_abs;
+            u32 pc = (u32)__popcll(w & SA_LSB_MASK);
+            if (FILTER && !payload_keep(w, a.min_payload, a.max_payload)) pc = 0;
+            const u32 packed = (rel << 5) | pc;
+            u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
+            const u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
+            const u32 next2 = __shfl_down_sync(0xffffffffu, packed, 2);
+            const u32 s = lo + warp * OWN;
+            if (lane == 0) {
+                prev = ~0u;
+                if (s > lo && s < hi) prev = ((u32)(__ldg(words + s - 1) >> SA_KEY_SHIFT) - tile_doc0_abs) << 5;
+            }
+            if (lane < OWN && i < hi && (prev >> 5) != rel && rel < SA_TILE_DOCS) {
+                u32 tf = pc;
+                if ((next >> 5) == rel) {
+                    tf += next & 31u;
+                    if ((next2 >> 5) == rel) {
+                        tf += next2 & 31u;
+                        for (u32 j = i + 3; j < n_words; j++) {
+                            const u64 w2 = __ldg(words + j);
+                            if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
+                            if (!(FILTER && !payload_keep(w2, a.min_payload, a.max_payload))) tf += (u32)__popcll(w2 & SA_LSB_MASK);
+                        }
+                    }
+                }
+                if (tf) {
+                    v = (MODE == TERM_MODE_TF) ? (float)tf : bm25_from_norm((float)tf, __ldg(a.norm + tile_doc0 + rel), tq.idf);
+                    my_rel = rel;
+                    a.out[(u64)q * a.out_stride + tile_doc0 + rel] = v;
+                }
+            }
+        }
+        if (!k) return;
+        const u32 my_bits = (v > 0.0f) ? __float_as_uint(v) : 0u;
+        const bool need_bound = (hi - lo) > k;                          // <= k words: all fit
+        if (need_bound) {
+            const u32 M = (k <= 10) ? 4u : 8u;
+            u32 mv = my_bits;
+            for (u32 r = 0; r < M; r++) {
+                u32 m = warp_pop_max(mv);
+                if (lane == r) s_top[warp * 8 + r] = m;
+            }
+            __syncthreads();
+        }
+        u32 thr = 1u;
+        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
+        if (my_bits >= thr) {
+            u32 slot = atomicAdd(&s_ncand, 1u);
+            if (slot < a.topk.slots)
+                a.topk.tile_cand[((u64)q * a.topk.n_tiles + tile) * a.topk.slots + slot] =
+                    ((u64)my_bits << 32) | (u64)(0xFFFFFFFFu - (tile_doc0 + my_rel));
+            atomicMax(&s_tile_max, my_bits);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const u32 n = s_ncand;
+            const u64 t_idx = (u64)q * a.topk.n_tiles + tile;
+            a.topk.tile_cnt[t_idx] = min(n, a.topk.slots);
+            a.topk.tile_max[t_idx] = s_tile_max;
+            if (n > a.topk.slots) a.topk.overflow[q] = 1u;
+        }
+        return;
+    }
+
+    // 1c. general path: build the tile in shared memory
+#pragma unroll
+    for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
+        reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
 
     // 2. stream the slice.  Each warp takes windows of 30 owned words and loads 32 (two look-ahead
     //    lanes), so "is the previous / next word the same doc?" is a register shuffle with no
@@ -120,8 +205,6 @@ term_tile_kernel(const TermBatchArgs a) {
     //    gathers are issued back to back before any score is computed (memory-level parallelism).
     u32 my_max = 0;
     const float *__restrict__ norm = a.norm + tile_doc0;
-    constexpr u32 OWN = 30;
-    constexpr u32 WIN = (SA_TERM_THREADS / 32) * OWN;                  // words per CTA pass (240)
     auto windows = [&](auto unroll_tag, const u32 base) {
         constexpr int UN = decltype(unroll_tag)::value;
         u64 w[UN];
@@ -201,7 +284,6 @@ term_tile_kernel(const TermBatchArgs a) {
     // 3. top-k.  A tile with no more words than candidate slots needs no bound: every positive
     //    score fits.  Otherwise each warp publishes its largest thread maxima and every warp
     //    derives the same tile bound; scores >= bound are this tile's candidates.
-    const u32 k = a.topk.k;
     const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
     if (need_bound) {
         const u32 M = (k <= 10) ? 4u : 8u;
@@ -224,7 +306,6 @@ term_tile_kernel(const TermBatchArgs a) {
 
     // 4. flush the tile: 16-byte streaming stores (the padded buffer makes the tile always in bounds)
     u32 cand_max = 0;
-    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
 #pragma unroll
     for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
         const unsigned g = tid + jj * SA_TERM_THREADS;
