@@ -74,184 +74,43 @@ __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k)
     return kth;
 }
 
-// head test + run sum for the word held by this lane (register-shuffle neighbours; see step 2)
-template <bool FILTER>
-__device__ __forceinline__ bool window_head(const TermBatchArgs &a, const u64 *__restrict__ words, u32 n_words,
-                                            u64 w, u32 i, u32 s, u32 lo, u32 hi, u32 doc0_abs, u32 rel_limit,
-                                            u32 &rel_out, u32 &tf_out) {
-    const unsigned lane = threadIdx.x & 31;
-    const u32 rel = (u32)(w >> SA_KEY_SHIFT) - doc0_abs;            // >= 2^27 for the ~0 filler
-    u32 pc = (u32)__popcll(w & SA_LSB_MASK);
-    if (FILTER && !payload_keep(w, a.min_payload, a.max_payload)) pc = 0;
-    const u32 packed = (rel << 5) | pc;                              // pc <= 18
-    u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
-    const u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
-    const u32 next2 = __shfl_down_sync(0xffffffffu, packed, 2);
-    if (lane == 0) {
-        prev = ~0u;                                                  // s == lo: previous word is another tile's
-        if (s > lo && s < hi) prev = ((u32)(__ldg(words + s - 1) >> SA_KEY_SHIFT) - doc0_abs) << 5;
-    }
-    if (!(lane < 30 && i < hi && (prev >> 5) != rel && rel < rel_limit)) return false;
-    u32 tf = pc;
-    if ((next >> 5) == rel) {
-        tf += next & 31u;
-        if ((next2 >> 5) == rel) {
-            tf += next2 & 31u;
-            for (u32 j = i + 3; j < n_words; j++) {                  // runs of >= 4 words (rare)
-                const u64 w2 = __ldg(words + j);
-                if ((u32)(w2 >> SA_KEY_SHIFT) - doc0_abs != rel) break;
-                if (!(FILTER && !payload_keep(w2, a.min_payload, a.max_payload))) tf += (u32)__popcll(w2 & SA_LSB_MASK);
-            }
-        }
-    }
-    rel_out = rel;
-    tf_out = tf;
-    return true;
-}
-
-#define SA_SUPER 4        // sub-tiles per CTA: a CTA owns a "super-tile" of SA_SUPER * SA_TILE_DOCS docs
-
 template <int MODE, bool ALL_DOCS, bool FILTER>
 __global__ void __launch_bounds__(SA_TERM_THREADS, 6)
 term_tile_kernel(const TermBatchArgs a) {
     __shared__ __align__(16) float s_out[SA_TILE_DOCS];
-    __shared__ u32 s_bounds[SA_SUPER + 1];
+    __shared__ u32 s_range[2];
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
 
     const u32 q = blockIdx.y;
+    const u32 tile = blockIdx.x;
     const TermQuery tq = a.queries[q];
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 *__restrict__ words = a.words + tq.word_off;
     const u32 n_words = (u32)tq.n_words;
-    const u32 n_tiles = (u32)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
-    const u32 sub0 = blockIdx.x * SA_SUPER;
-    const u32 n_sub = min((u32)SA_SUPER, n_tiles - sub0);
-    const u32 super_doc0 = sub0 * SA_TILE_DOCS;                       // local doc index
-    const u32 k = a.topk.k;
-    constexpr u32 OWN = 30;
-    constexpr u32 WIN = (SA_TERM_THREADS / 32) * OWN;                  // words per CTA pass (240)
-    float *__restrict__ out_row = a.out + (u64)q * a.out_stride;
-
-    // 1. posting slice boundaries of the sub-tiles: b[j] = first word of sub-tile sub0 + j
-    u32 b[SA_SUPER + 1];
-    if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
-        const u32 *dir = a.tile_dir + tq.dir_off + sub0;
-#pragma unroll
-        for (int j = 0; j <= SA_SUPER; j++) b[j] = __ldg(dir + min((u32)j, n_sub));
-    } else {
-        if (warp <= n_sub) {
-            u64 key = (u64)a.doc_base + (u64)(sub0 + warp) * SA_TILE_DOCS;
-            u64 r = warp_lower_bound_shifted(words, 0, n_words, key, SA_KEY_SHIFT);
-            if (lane == 0) s_bounds[warp] = (u32)r;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j <= SA_SUPER; j++) b[j] = s_bounds[min((u32)j, n_sub)];
-    }
-
-    // 1b. SPARSE SUPER-TILE (its words fit one unrolled pass): no shared-memory tile.  The zeros of
-    //     all its sub-tiles go straight to HBM at the start of the CTA -- one dir -> words -> norm
-    //     load chain is then paid per 16K docs instead of per 4K, which is what bounds sparse and
-    //     medium terms -- and the few scores are stored over them afterwards (they merge with the
-    //     zero lines in L2).  Each thread holds at most SA_TERM_UNROLL scores, in registers.
-    if (!ALL_DOCS && b[n_sub] - b[0] <= WIN * SA_TERM_UNROLL) {
-        const u32 lo = b[0], hi = b[n_sub];
-        const u32 super_abs = (u32)a.doc_base + super_doc0;
-        float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out_row + super_doc0);
-        const u32 n_vec = n_sub * (SA_TILE_DOCS / 4);
-#pragma unroll
-        for (int jj = 0; jj < SA_SUPER * SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
-            const u32 idx = tid + jj * SA_TERM_THREADS;
-            if (idx < n_vec) __stcs(out4 + idx, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-        if (k && tid == 0) { s_ncand = 0; s_tile_max = 0; }
-        __syncthreads();                       // zero stores are ordered before the score stores below
-        float v[SA_TERM_UNROLL];
-        u32 vrel[SA_TERM_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++) { v[u] = 0.0f; vrel[u] = 0; }
-        if (hi > lo) {
-            u64 w[SA_TERM_UNROLL];
-#pragma unroll
-            for (int u = 0; u < SA_TERM_UNROLL; u++) {
-                const u32 i = lo + (u * (SA_TERM_THREADS / 32) + warp) * OWN + lane;
-                w[u] = (i < n_words && i < hi + 2) ? __ldg(words + i) : ~0ull;
-            }
-            u32 tfs[SA_TERM_UNROLL];
-            float nr[SA_TERM_UNROLL];
-#pragma unroll
-            for (int u = 0; u < SA_TERM_UNROLL; u++) {
-                const u32 s = lo + (u * (SA_TERM_THREADS / 32) + warp) * OWN;
-                tfs[u] = 0;
-                nr[u] = 0.0f;
-                u32 rel, tf;
-                if (window_head<FILTER>(a, words, n_words, w[u], s + lane, s, lo, hi, super_abs, n_sub * SA_TILE_DOCS, rel, tf)) {
-                    tfs[u] = tf;
-                    vrel[u] = rel;
-                    if (MODE == TERM_MODE_SCORE && tf) nr[u] = __ldg(a.norm + super_doc0 + rel);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SA_TERM_UNROLL; u++) {
-                if (tfs[u]) {
-                    v[u] = (MODE == TERM_MODE_TF) ? (float)tfs[u] : bm25_from_norm((float)tfs[u], nr[u], tq.idf);
-                    out_row[super_doc0 + vrel[u]] = v[u];
-                }
-            }
-        }
-        if (!k) return;
-        u32 my_bits = 0;
-#pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++)
-            if (v[u] > 0.0f) my_bits = max(my_bits, __float_as_uint(v[u]));
-        const bool need_bound = (hi - lo) > k;                          // <= k words: all fit
-        if (need_bound) {
-            const u32 M = (k <= 10) ? 4u : 8u;
-            u32 mv = my_bits;
-            for (u32 r = 0; r < M; r++) {
-                u32 m = warp_pop_max(mv);
-                if (lane == r) s_top[warp * 8 + r] = m;
-            }
-            __syncthreads();
-        }
-        u32 thr = 1u;
-        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
-        // the super-tile's candidates all go to its first sub-tile's slots
-        u64 *__restrict__ my_cand = a.topk.tile_cand + ((u64)q * a.topk.n_tiles + sub0) * a.topk.slots;
-        u32 cand_max = 0;
-#pragma unroll
-        for (int u = 0; u < SA_TERM_UNROLL; u++) {
-            const u32 bits = __float_as_uint(v[u]);
-            if (v[u] > 0.0f && bits >= thr) {
-                u32 slot = atomicAdd(&s_ncand, 1u);
-                if (slot < a.topk.slots) my_cand[slot] = ((u64)bits << 32) | (u64)(0xFFFFFFFFu - (super_doc0 + vrel[u]));
-                cand_max = max(cand_max, bits);
-            }
-        }
-        if (cand_max) atomicMax(&s_tile_max, cand_max);
-        __syncthreads();
-        if (tid < n_sub) {
-            const u64 t_idx = (u64)q * a.topk.n_tiles + sub0 + tid;
-            const u32 n = s_ncand;
-            a.topk.tile_cnt[t_idx] = tid == 0 ? min(n, a.topk.slots) : 0u;
-            a.topk.tile_max[t_idx] = tid == 0 ? s_tile_max : 0u;
-            if (tid == 0 && n > a.topk.slots) a.topk.overflow[q] = 1u;
-        }
-        return;
-    }
-
-    // 1c. general path: the sub-tiles one after the other, each built in shared memory
-    for (u32 sub = 0; sub < n_sub; sub++) {
-    const u32 tile = sub0 + sub;
-    const u32 lo = b[sub], hi = b[sub + 1];
     const u32 tile_doc0 = tile * SA_TILE_DOCS;                       // local doc index
     const u32 tile_doc0_abs = (u32)a.doc_base + tile_doc0;           // as stored in the words
-    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out_row + tile_doc0);
+
+    // 1. zero the tile; posting slice [lo, hi) of this tile
 #pragma unroll
     for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
         reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+    u32 lo, hi;
+    if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
+        const u32 *dir = a.tile_dir + tq.dir_off + tile;
+        lo = __ldg(dir);
+        hi = __ldg(dir + 1);
+        __syncthreads();
+    } else {
+        if (warp < 2) {
+            u64 key = (u64)tile_doc0_abs + (warp ? SA_TILE_DOCS : 0);
+            u64 r = warp_lower_bound_shifted(words, 0, n_words, key, SA_KEY_SHIFT);
+            if (lane == 0) s_range[warp] = (u32)r;
+        }
+        __syncthreads();
+        lo = s_range[0];
+        hi = s_range[1];
+    }
 
     // 2. stream the slice.  Each warp takes windows of 30 owned words and loads 32 (two look-ahead
     //    lanes), so "is the previous / next word the same doc?" is a register shuffle with no
@@ -261,6 +120,8 @@ term_tile_kernel(const TermBatchArgs a) {
     //    gathers are issued back to back before any score is computed (memory-level parallelism).
     u32 my_max = 0;
     const float *__restrict__ norm = a.norm + tile_doc0;
+    constexpr u32 OWN = 30;
+    constexpr u32 WIN = (SA_TERM_THREADS / 32) * OWN;                  // words per CTA pass (240)
     auto windows = [&](auto unroll_tag, const u32 base) {
         constexpr int UN = decltype(unroll_tag)::value;
         u64 w[UN];
@@ -270,39 +131,63 @@ term_tile_kernel(const TermBatchArgs a) {
             // look-ahead lanes may read into the next tile (another doc) but never past the list
             w[u] = (i < n_words && i < hi + 2) ? __ldg(words + i) : ~0ull;
         }
-        u32 rl[UN], tfv[UN];
+        u32 pk[UN];                                       // rel << 18 | tf, ~0 = not a head
         float nr[UN];
 #pragma unroll
         for (int u = 0; u < UN; u++) {
             const u32 s = base + (u * (SA_TERM_THREADS / 32) + warp) * OWN;   // window start (warp-uniform)
-            rl[u] = ~0u;
-            tfv[u] = 0;
+            const u32 i = s + lane;
+            const u32 rel = (u32)(w[u] >> SA_KEY_SHIFT) - tile_doc0_abs;  // >= 2^27 for the ~0 filler
+            u32 pc = (u32)__popcll(w[u] & SA_LSB_MASK);
+            if (FILTER && !payload_keep(w[u], a.min_payload, a.max_payload)) pc = 0;
+            const u32 packed = (rel << 5) | pc;                        // pc <= 18
+            u32 prev = __shfl_up_sync(0xffffffffu, packed, 1);
+            const u32 next = __shfl_down_sync(0xffffffffu, packed, 1);
+            const u32 next2 = __shfl_down_sync(0xffffffffu, packed, 2);
+            if (lane == 0) {
+                prev = ~0u;                                           // s == lo: previous word is another tile's
+                if (s > lo && s < hi) prev = ((u32)(__ldg(words + s - 1) >> SA_KEY_SHIFT) - tile_doc0_abs) << 5;
+            }
+            pk[u] = ~0u;
             nr[u] = 0.0f;
-            u32 rel, tf;
-            if (window_head<FILTER>(a, words, n_words, w[u], s + lane, s, lo, hi, tile_doc0_abs, SA_TILE_DOCS, rel, tf)) {
-                rl[u] = rel;
-                tfv[u] = tf;
+            const bool owned = lane < OWN && i < hi;
+            if (owned && (prev >> 5) != rel && rel < SA_TILE_DOCS) {
+                u32 tf = pc;
+                if ((next >> 5) == rel) {
+                    tf += next & 31u;
+                    if ((next2 >> 5) == rel) {
+                        tf += next2 & 31u;
+                        for (u32 j = i + 3; j < n_words; j++) {        // runs of >= 4 words (rare)
+                            const u64 w2 = __ldg(words + j);
+                            if ((u32)(w2 >> SA_KEY_SHIFT) - tile_doc0_abs != rel) break;
+                            if (!(FILTER && !payload_keep(w2, a.min_payload, a.max_payload))) tf += (u32)__popcll(w2 & SA_LSB_MASK);
+                        }
+                    }
+                }
+                pk[u] = (rel << 18) | tf;
                 if (MODE == TERM_MODE_SCORE && !ALL_DOCS && tf) nr[u] = __ldg(norm + rel);
             }
         }
 #pragma unroll
         for (int u = 0; u < UN; u++) {
-            if (rl[u] != ~0u) {
+            if (pk[u] != ~0u) {
+                const u32 rel = pk[u] >> 18, tf = pk[u] & 0x3FFFFu;
                 float v;
                 if (MODE == TERM_MODE_TF || ALL_DOCS) {
-                    v = (float)tfv[u];
+                    v = (float)tf;
                 } else {
                     v = 0.0f;
-                    if (tfv[u]) {
-                        v = bm25_from_norm((float)tfv[u], nr[u], tq.idf);
+                    if (tf) {
+                        v = bm25_from_norm((float)tf, nr[u], tq.idf);
                         my_max = max(my_max, __float_as_uint(v));
                     }
                 }
-                s_out[rl[u]] = v;
+                s_out[rel] = v;
             }
         }
     };
-    // CTA-uniform schedule: big slices in 4-window passes, the remainder in single-window passes
+    // CTA-uniform schedule: big slices in 4-window passes, the remainder (and small tiles) in
+    // single-window passes so sparse tiles do not pay for empty windows.
     u32 base = lo;
     while (base < hi && hi - base > WIN) {
         windows(std::integral_constant<int, SA_TERM_UNROLL>{}, base);
@@ -313,10 +198,11 @@ term_tile_kernel(const TermBatchArgs a) {
         base += WIN;
     }
 
-    // 3. top-k.  A tile with no more than k words needs no bound: every positive score fits.
-    //    Otherwise each warp publishes its largest thread maxima and every warp derives the same
-    //    tile bound; scores >= bound are this tile's candidates.
-    const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform
+    // 3. top-k.  A tile with no more words than candidate slots needs no bound: every positive
+    //    score fits.  Otherwise each warp publishes its largest thread maxima and every warp
+    //    derives the same tile bound; scores >= bound are this tile's candidates.
+    const u32 k = a.topk.k;
+    const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
     if (need_bound) {
         const u32 M = (k <= 10) ? 4u : 8u;
         u32 v = my_max;
@@ -338,6 +224,7 @@ term_tile_kernel(const TermBatchArgs a) {
 
     // 4. flush the tile: 16-byte streaming stores (the padded buffer makes the tile always in bounds)
     u32 cand_max = 0;
+    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.out + (u64)q * a.out_stride + tile_doc0);
 #pragma unroll
     for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
         const unsigned g = tid + jj * SA_TERM_THREADS;
@@ -381,8 +268,6 @@ term_tile_kernel(const TermBatchArgs a) {
             a.topk.tile_max[t_idx] = s_tile_max;
             if (n > a.topk.slots) a.topk.overflow[q] = 1u;
         }
-    }
-    __syncthreads();           // the shared tile and counters are reused by the next sub-tile
     }
 }
 
@@ -498,8 +383,7 @@ int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
         if (rc) return rc;
         a.norm = ix->d_norm;
     }
-    const unsigned n_tiles = (unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
-    dim3 grid((n_tiles + SA_SUPER - 1) / SA_SUPER, n_queries);
+    dim3 grid((unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS), n_queries);
     dim3 block(SA_TERM_THREADS);
     KernelTimer t(ix, 0);
     if (a.mode == TERM_MODE_TF) {

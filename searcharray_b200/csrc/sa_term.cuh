@@ -2,7 +2,7 @@
 #pragma once
 #include "sa_common.cuh"
 
-#define SA_TILE_DOCS 4096          // docs per CTA tile (16 KB of float32 scores)
+#define SA_TILE_DOCS 8192          // docs per CTA tile (32 KB of float32 scores)
 #define SA_TERM_UNROLL 4           // 30-word windows loaded per warp before processing
 #define SA_TERM_THREADS 256
 #define SA_TOPK_MAX 32             // warp-level threshold estimation handles k <= 32
