@@ -551,7 +551,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
         C.n_phrase = (u32)B.pqs.size() - C.phrase0;
         if (C.n_phrase) {
             u64 want = std::max<u64>(1, (u64)ix->num_sms * 16 / C.n_phrase);
-            C.phrase_chunks = (u32)std::max<u64>(1, std::min<u64>(want, std::max<u64>(1, ix->n_docs / 512)));
+            C.phrase_chunks = sa_phrase_chunks(ix, (u32)std::max<u64>(1, std::min<u64>(want, std::max<u64>(1, ix->n_docs / 512))));
             for (u32 i = 0; i < C.n_phrase; i++)
                 C.arena_words += sa_phrase_arena_words(B.pqs[C.phrase0 + i], C.phrase_chunks);
             max_arena = std::max(max_arena, C.arena_words);
@@ -603,12 +603,11 @@ int sa_batch_execute_locked(sa_index *ix) {
         if (C.n_phrase) {
             float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;
             unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
-            SA_CUDA(cudaMemsetAsync(rows, 0, (size_t)C.n_phrase * stride * sizeof(float), ix->stream));
             SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
+            // the phrase kernel materialises its dense rows (zeros + matches) and their top-k candidates
             if ((rc = sa_phrase_enqueue(ix, B.d_pq.as<PhraseQuery>() + C.phrase0, B.d_pstats.as<PhraseStats>() + C.phrase0,
                                         C.n_phrase, rows, stride, C.phrase_chunks, (u64 *)ix->phrase_scratch.p + 8,
-                                        d_used, C.arena_words, 1, C.params))) return rc;
-            if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, C.n_term, C.n_phrase, t))) return rc;
+                                        d_used, C.arena_words, 1, C.params, &t, C.n_term))) return rc;
         }
         if ((rc = launch_topk_select(ix, t, Q, ix->doc_base, d_keys, B.d_row_query.as<u32>() + C.row0))) return rc;
     }

@@ -36,6 +36,8 @@ int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
 
 #define PT SA_PHRASE_THREADS
 
+static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks);
+
 struct Elem {
     u64 w0, w1;
     u32 n_emit, cnt, doc;
@@ -314,6 +316,10 @@ phrase_kernel(const PhraseArgs a) {
     __shared__ u64 s_lo[SA_MAX_PHRASE_TERMS], s_n[SA_MAX_PHRASE_TERMS];
     __shared__ u64 s_slab;
     __shared__ int s_ok;
+    __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
+    __shared__ u32 s_top[(PT / 32) * 8];
+    __shared__ u32 s_ncand, s_tile_max;
+    __shared__ u64 s_m[2];
 
     const u32 q = blockIdx.y;
     const PhraseQuery &pq = a.queries[q];
@@ -321,8 +327,11 @@ phrase_kernel(const PhraseArgs a) {
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 d0 = a.doc_base + (u64)blockIdx.x * a.docs_per_chunk;
     const u64 dend = a.doc_base + a.n_docs;
-    if (d0 >= dend) return;
+    if (d0 >= dend) return;                    // (grid is sized so this does not happen)
     const u64 d1 = min(d0 + a.docs_per_chunk, dend);
+    ChainResult fin;
+    fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
+    bool run = true;
 
     // 1. every term's slice for this doc range
     for (u32 t = warp; t < n_terms; t += PT / 32) {
@@ -340,19 +349,23 @@ phrase_kernel(const PhraseArgs a) {
     // A chunk where fewer than two terms occur has no pairs at any step.  (A chunk that merely
     // misses ONE term must still run its earlier steps: their pairs count towards the global
     // same-term decision of the reference.)
-    if (widest < 2) return;
+    if (widest < 2) run = false;
     cap += 2;
 
     // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers
     if (tid == 0) {
-        unsigned long long need = 6ull * cap;
-        unsigned long long at = atomicAdd(a.arena_used, need);
-        s_ok = (at + need <= a.arena_cap);
-        s_slab = at;
-        if (!s_ok) atomicExch(&a.stats[q].overflow, 1u);
+        s_ok = 1;
+        s_slab = 0;
+        if (run) {
+            unsigned long long need = 6ull * cap;
+            unsigned long long at = atomicAdd(a.arena_used, need);
+            s_ok = (at + need <= a.arena_cap);
+            s_slab = at;
+            if (!s_ok) atomicExch(&a.stats[q].overflow, 1u);
+        }
     }
     __syncthreads();
-    if (!s_ok) return;
+    if (!s_ok) run = false;
     u64 *contA = a.arena + s_slab, *contB = contA + cap;
     u64 *docsA = contB + cap, *docsB = docsA + cap, *docsL = docsB + cap, *docsR = docsL + cap;
 
@@ -418,7 +431,7 @@ phrase_kernel(const PhraseArgs a) {
         return res;
     };
 
-    ChainResult fin;
+    if (run) {
     if (pq.mode == SA_PHRASE_MODE_LR) {
         fin = run_chain(0, n_terms, true, docsL);
     } else if (pq.mode == SA_PHRASE_MODE_RL) {
@@ -431,6 +444,7 @@ phrase_kernel(const PhraseArgs a) {
         and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
     }
 
+    }
     // optional dump for the per-op parity export (single chunk)
     if (a.dump.cont) {
         for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
@@ -438,17 +452,45 @@ phrase_kernel(const PhraseArgs a) {
         if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
     }
 
-    // 3. scatter the matches into the dense vector (phrase_freqs[ids] = counts, middle_out.py:441)
+    // 3. materialise the dense vector of this doc range tile by tile (phrase_freqs[ids] = counts,
+    //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
+    //    streaming stores; the same pass collects the tile's top-k candidates.
     float *out = a.out + (u64)q * a.out_stride;
     Bm25Params p = a.bm25;
     p.idf = pq.idf;
-    for (u64 i = tid; i < fin.n_docs; i += PT) {
-        u64 e = fin.docs[i];
-        u32 c = (u32)(e & 0xFFFFFFFFull);
-        if (c == 0) continue;
-        u64 d = (e >> 32) - a.doc_base;
-        if (d >= a.n_docs) continue;
-        out[d] = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+    const u32 row = a.topk_row0 + q;
+    const u32 tile0 = (u32)(((u64)blockIdx.x * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    for (u32 tile = tile0; tile < tile1; tile++) {
+        const u64 t_abs0 = a.doc_base + (u64)tile * SA_TILE_DOCS, t_abs1 = t_abs0 + SA_TILE_DOCS;
+        if (tid < 2) {               // entries of fin.docs (sorted by doc) inside this tile
+            const u64 key = tid ? t_abs1 : t_abs0;
+            u64 lo = 0, hi = fin.n_docs;
+            while (lo < hi) {
+                u64 mid = (lo + hi) >> 1;
+                if ((fin.docs[mid] >> 32) < key) lo = mid + 1; else hi = mid;
+            }
+            s_m[tid] = lo;
+        }
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+            reinterpret_cast<float4 *>(s_tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        const u64 m0 = s_m[0], m1 = s_m[1];
+        u32 my_max = 0;
+        for (u64 i = m0 + tid; i < m1; i += PT) {
+            const u64 e = fin.docs[i];
+            const u32 c = (u32)(e & 0xFFFFFFFFull);
+            if (c == 0) continue;
+            const u64 d = (e >> 32) - a.doc_base;
+            if (d >= a.n_docs) continue;
+            const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+            s_tile[d - (u64)tile * SA_TILE_DOCS] = v;
+            if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+        }
+        __syncthreads();
+        flush_tile_collect(s_tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
+                           s_top, &s_ncand, &s_tile_max);
     }
 }
 
@@ -522,7 +564,8 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         n_chunks = (u32)std::min<u64>(want, std::max<u64>(1, ix->n_docs / 512));
         n_chunks = std::max<u32>(n_chunks, 1);
     }
-    const u64 docs_per_chunk = (ix->n_docs + n_chunks - 1) / n_chunks;
+    n_chunks = sa_phrase_chunks(ix, n_chunks);
+    const u64 docs_per_chunk = docs_per_chunk_of(ix, n_chunks);
     u64 arena_words = 64;
     for (auto &pq : pqs) {
         u64 sum = 0;
@@ -540,8 +583,7 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         SA_CUDA(cudaMemcpyAsync(ix->queries.p, pqs.data(), (size_t)Q * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
         SA_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)Q * sizeof(PhraseStats), ix->stream));
         SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
-        SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, (size_t)Q * stride * sizeof(float), ix->stream));
-        PhraseArgs a;
+        PhraseArgs a;      // (the kernel writes every tile of the dense rows itself: no zero-fill pass)
         memset(&a, 0, sizeof(a));
         a.words = d_words;
         a.doc_lens = ix->d_doc_lens;
@@ -606,9 +648,22 @@ u64 sa_phrase_arena_words(const PhraseQuery &pq, u32 n_chunks) {
 
 // Asynchronous launch of already planned phrase queries living in device memory; dense rows,
 // stats and the arena counter must have been zeroed by the caller.
+// chunks are whole tiles: returns the chunk count actually used for `wanted` chunks per query
+u32 sa_phrase_chunks(const sa_index *ix, u32 wanted) {
+    const u64 n_tiles = (ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS;
+    const u64 tiles_per_chunk = std::max<u64>(1, (n_tiles + std::max<u32>(wanted, 1) - 1) / std::max<u32>(wanted, 1));
+    return (u32)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+}
+
+static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks) {
+    const u64 n_tiles = (ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS;
+    return ((n_tiles + n_chunks - 1) / n_chunks) * SA_TILE_DOCS;
+}
+
 int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_stats, u32 Q,
                       float *dense_rows, u64 stride, u32 n_chunks, u64 *d_arena,
-                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p) {
+                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p,
+                      const TopkCtx *topk, u32 topk_row0) {
     PhraseArgs a;
     memset(&a, 0, sizeof(a));
     a.words = ix->d_words;
@@ -620,12 +675,14 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
     a.out = dense_rows;
     a.out_stride = stride;
     a.n_chunks = n_chunks;
-    a.docs_per_chunk = (ix->n_docs + n_chunks - 1) / n_chunks;
+    a.docs_per_chunk = docs_per_chunk_of(ix, n_chunks);
     a.arena = d_arena;
     a.arena_used = d_arena_used;
     a.arena_cap = arena_words;
     a.bm25 = p;
     a.score = score;
+    if (topk) a.topk = *topk;
+    a.topk_row0 = topk_row0;
     return launch_phrase(ix, a, Q);
 }
 

@@ -1,6 +1,7 @@
 // sa_phrase.cuh -- declarations for the phrase (slop == 0) path.
 #pragma once
 #include "sa_common.cuh"
+#include "sa_term.cuh"
 
 #define SA_PHRASE_THREADS 256
 #define SA_PHRASE_MODE_LR 0      // left-to-right chain  (reference middle_out.py:96-122)
@@ -50,6 +51,12 @@ struct PhraseArgs {
     Bm25Params bm25;
     int score;                  // 0: write phrase freqs, 1: BM25 (sparse)
     PhraseDump dump;
+    // Every CTA writes the dense tiles of its doc range itself (zeros + matches) -- no separate
+    // zero-fill pass -- and, when topk.k != 0, collects their top-k candidates on the way.
+    // docs_per_chunk is a multiple of SA_TILE_DOCS.  topk.overflow / tile arrays are indexed by
+    // row = topk_row0 + query.
+    TopkCtx topk;
+    u32 topk_row0;
 };
 
 int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries);
@@ -58,6 +65,8 @@ bool sa_phrase_guess_ok(PhraseQuery &pq, const PhraseStats &st);
 u64 sa_phrase_arena_words(const PhraseQuery &pq, u32 n_chunks);
 int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_stats, u32 Q,
                       float *dense_rows, u64 stride, u32 n_chunks, u64 *d_arena,
-                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p);
+                      unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p,
+                      const TopkCtx *topk, u32 topk_row0);
+u32 sa_phrase_chunks(const sa_index *ix, u32 wanted);
 int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
                        int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump);

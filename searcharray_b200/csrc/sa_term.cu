@@ -42,38 +42,6 @@ __device__ __forceinline__ float bm25_from_norm(float tf, float norm, float idf)
     return __fmul_rn(__fdiv_rn(tf, __fadd_rn(tf, norm)), idf);
 }
 
-// The j-th round of "take the warp maximum, then clear it" (REDUX.MAX: one instruction per
-// round on sm_80+).  Equal values collapse into one, which can only lower the resulting bound
-// -- it stays a valid lower bound of the k-th best score.
-__device__ __forceinline__ u32 warp_pop_max(u32 &v) {
-    u32 m = __reduce_max_sync(0xffffffffu, v);
-    if (v == m) v = 0;
-    return m;
-}
-
-// k-th largest (k <= 32) of the CTA's thread maxima, from the per-warp top-M lists in shared
-// memory (M = 4 for k <= 10 else 8; exact unless one warp holds more than M of the CTA's top k).
-// Every warp computes it redundantly (~4k instructions... 4 per round), no extra barrier.
-__device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k) {
-    const unsigned lane = threadIdx.x & 31;
-    u32 v0, v1 = 0;
-    if (k <= 10) {
-        v0 = s_top[(lane >> 2) * 8 + (lane & 3)];
-    } else {
-        v0 = s_top[lane];
-        v1 = s_top[32 + lane];
-    }
-    u32 kth = 0;
-    for (u32 r = 0; r < k; r++) {
-        u32 m0 = __reduce_max_sync(0xffffffffu, max(v0, v1));
-        if (v0 == m0) v0 = 0;
-        else if (v1 == m0) v1 = 0;
-        kth = m0;
-        if (m0 == 0) break;
-    }
-    return kth;
-}
-
 template <int MODE, bool ALL_DOCS, bool FILTER>
 __global__ void __launch_bounds__(SA_TERM_THREADS, 6)
 term_tile_kernel(const TermBatchArgs a) {

@@ -53,3 +53,100 @@ int sa_batch_execute_locked(sa_index *ix);
 int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone);
 void sa_batch_dims(sa_index *ix, u32 *nq, u32 *k);
 void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_scores);
+
+#ifdef __CUDACC__
+// The j-th round of "take the warp maximum, then clear it" (REDUX.MAX: one instruction per
+// round on sm_80+).  Equal values collapse into one, which can only lower the resulting bound
+// -- it stays a valid lower bound of the k-th best score.
+__device__ __forceinline__ u32 warp_pop_max(u32 &v) {
+    u32 m = __reduce_max_sync(0xffffffffu, v);
+    if (v == m) v = 0;
+    return m;
+}
+
+// k-th largest (k <= 32) of the CTA's thread maxima, from the per-warp top-M lists in shared
+// memory (M = 4 for k <= 10 else 8; exact unless one warp holds more than M of the CTA's top k).
+// Every warp computes it redundantly (~4k instructions... 4 per round), no extra barrier.
+__device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k) {
+    const unsigned lane = threadIdx.x & 31;
+    u32 v0, v1 = 0;
+    if (k <= 10) {
+        v0 = s_top[(lane >> 2) * 8 + (lane & 3)];
+    } else {
+        v0 = s_top[lane];
+        v1 = s_top[32 + lane];
+    }
+    u32 kth = 0;
+    for (u32 r = 0; r < k; r++) {
+        u32 m0 = __reduce_max_sync(0xffffffffu, max(v0, v1));
+        if (v0 == m0) v0 = 0;
+        else if (v1 == m0) v1 = 0;
+        kth = m0;
+        if (m0 == 0) break;
+    }
+    return kth;
+}
+
+
+// Flush one shared-memory score tile to its dense row with 16-byte streaming stores and, on the way,
+// collect the tile's top-k candidates (private slots, count, maximum): the same step the term kernel
+// ends with, shared with the phrase kernel.  `my_max` = largest score bits this thread put into the
+// tile, `n_items` = number of scores in the tile.  All SA_TERM_THREADS threads must call.
+__device__ __forceinline__ void flush_tile_collect(const float *s_out, float *__restrict__ out_tile, const TopkCtx &t,
+                                                   u32 row, u32 tile, u32 my_max, u32 n_items, u32 *s_top,
+                                                   u32 *s_ncand, u32 *s_tile_max) {
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u32 k = t.k;
+    const u32 tile_doc0 = tile * SA_TILE_DOCS;
+    const bool need_bound = k && n_items > k;                        // CTA-uniform
+    if (need_bound) {
+        const u32 M = (k <= 10) ? 4u : 8u;
+        u32 v = my_max;
+        for (u32 r = 0; r < M; r++) {
+            u32 m = warp_pop_max(v);
+            if (lane == r) s_top[warp * 8 + r] = m;
+        }
+    }
+    if (k && tid == 0) { *s_ncand = 0; *s_tile_max = 0; }
+    __syncthreads();
+    float thr_f = 0.0f;
+    if (k) {
+        u32 thr = 1u;
+        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
+        thr_f = __uint_as_float(thr);
+    }
+    u64 *__restrict__ my_cand = k ? t.tile_cand + ((u64)row * t.n_tiles + tile) * t.slots : nullptr;
+    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out_tile);
+    u32 cand_max = 0;
+#pragma unroll
+    for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
+        const unsigned g = tid + jj * SA_TERM_THREADS;
+        const float4 v = reinterpret_cast<const float4 *>(s_out)[g];
+        __stcs(out4 + g, v);
+        if (k && ((v.x >= thr_f) | (v.y >= thr_f) | (v.z >= thr_f) | (v.w >= thr_f))) {
+            const float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (vs[e] >= thr_f) {
+                    u32 slot = atomicAdd(s_ncand, 1u);
+                    if (slot < t.slots)
+                        my_cand[slot] = ((u64)__float_as_uint(vs[e]) << 32) | (u64)(0xFFFFFFFFu - (tile_doc0 + g * 4 + e));
+                    cand_max = max(cand_max, __float_as_uint(vs[e]));
+                }
+            }
+        }
+    }
+    if (k) {
+        if (cand_max) atomicMax(s_tile_max, cand_max);
+        __syncthreads();
+        if (tid == 0) {
+            const u32 n = *s_ncand;
+            const u64 t_idx = (u64)row * t.n_tiles + tile;
+            t.tile_cnt[t_idx] = min(n, t.slots);
+            t.tile_max[t_idx] = *s_tile_max;
+            if (n > t.slots) t.overflow[row] = 1u;
+        }
+    }
+    __syncthreads();
+}
+#endif
