@@ -368,46 +368,56 @@ def bench_ours(args, rank, world):
         p_docs = np.empty((PQ, k), dtype=np.uint32)
         p_scores = np.empty((PQ, k), dtype=np.float32)
 
-        def p_upload():
-            _lib.check(L.sa_batch_upload(h, _lib.p_u32(p_terms), _lib.p_u32(p_starts), _lib.p_f32(p_idf), PQ, 0,
-                                         float(avgdl), K1, B, k))
-
-        def p_download():
-            if world > 1:
-                _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
-            else:
-                _lib.check(L.sa_batch_download(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
-            return n_over.value
-
-        p_redo = 0
-        for _ in range(3):
-            p_upload(); execute(); p_redo += p_download()
-        p_upload()
-        _lib.check(L.sa_stats_reset(h))
-        barrier()
-        _lib.check(L.sa_timer_start(h))
-        p_steps = max(2, args.steps)
-        for _ in range(p_steps):
-            execute()
-        _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
-        barrier()
-        p_ms = max_over_ranks(ms.value)
-        p_download()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(p_steps):
-            p_upload(); execute(); p_redo += p_download()
-        barrier()
-        p_e2e_s = max_over_ranks(time.perf_counter() - t0)
         Wp = np.asarray([[host.term_lengths[spec.term_index[t]] for t in ph] for ph in pq_names], dtype=np.float64)
-        phrase = {"workload": "4-term phrase, slop 0 (BASELINE configs[2]), planted phrases, top-%d" % k,
-                  "queries_per_step": PQ, "value": p_steps * PQ / (p_ms / 1e3), "unit": "queries/s",
-                  "ms_per_step": p_ms / p_steps,
-                  "e2e": {"value": p_steps * PQ / p_e2e_s, "unit": "queries/s"},
-                  "mean_words_per_query_this_shard": float(np.mean(np.sum(Wp, axis=1))),
-                  "min_list_words_mean": float(np.mean(np.min(Wp, axis=1))),
-                  "repairs": int(p_redo),
-                  "matches_in_top1": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF))}
+
+        def phrase_block(slop):
+            """One batched pass family of the PQ phrase queries with `slop`: device-timed steps, then the
+            same steps end to end (upload + execute + top-k download)."""
+            def p_upload():
+                _lib.check(L.sa_batch_upload(h, _lib.p_u32(p_terms), _lib.p_u32(p_starts), _lib.p_f32(p_idf), PQ, slop,
+                                             float(avgdl), K1, B, k))
+
+            def p_download():
+                if world > 1:
+                    _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
+                else:
+                    _lib.check(L.sa_batch_download(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
+                return n_over.value
+
+            p_redo = 0
+            for _ in range(3):
+                p_upload(); execute(); p_redo += p_download()
+            p_upload()
+            _lib.check(L.sa_stats_reset(h))
+            barrier()
+            _lib.check(L.sa_timer_start(h))
+            p_steps = max(2, args.steps)
+            for _ in range(p_steps):
+                execute()
+            _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
+            barrier()
+            p_ms = max_over_ranks(ms.value)
+            p_download()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(p_steps):
+                p_upload(); execute(); p_redo += p_download()
+            barrier()
+            p_e2e_s = max_over_ranks(time.perf_counter() - t0)
+            return {"queries_per_step": PQ, "value": p_steps * PQ / (p_ms / 1e3), "unit": "queries/s",
+                    "ms_per_step": p_ms / p_steps,
+                    "e2e": {"value": p_steps * PQ / p_e2e_s, "unit": "queries/s"},
+                    "repairs": int(p_redo),
+                    "matches_in_top1": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF))}
+
+        phrase = {"workload": "4-term phrase, slop 0 (BASELINE configs[2]), planted phrases, top-%d" % k}
+        phrase.update(phrase_block(0))
+        phrase["mean_words_per_query_this_shard"] = float(np.mean(np.sum(Wp, axis=1)))
+        phrase["min_list_words_mean"] = float(np.mean(np.min(Wp, axis=1)))
+        slop2_batch = None
+        if args.slop_queries > 0:
+            slop2_batch = {"workload": "4-term phrase, slop 2 (BASELINE configs[3]), same batched top-%d API" % k}
+            slop2_batch.update(phrase_block(2))
         # slop = 2 (BASELINE configs[3]) goes through the per-query C-ABI call: span search is
         # latency/branch bound (SURVEY 8d: informational, no roofline expectation)
         if rank == 0 and world == 1 and args.slop_queries > 0:
@@ -426,11 +436,13 @@ def bench_ours(args, rank, world):
                 matched += int(np.count_nonzero(out))
             _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
             _lib.check(L.sa_set_profiling(h, 0))
-            phrase["slop2"] = {"workload": "4-term phrase, slop 2 (BASELINE configs[3]), sa_score_phrase per query, "
-                                           "dense float32[N] to the host", "queries": ns,
-                               "e2e": {"value": ns / dt, "unit": "queries/s"},
-                               "kernel_ms_per_query": stats.phrase_kernel_ms / ns,
-                               "mean_matching_docs": matched / ns}
+            phrase["slop2_dense"] = {"workload": "4-term phrase, slop 2, sa_score_phrase per query (the .score() drop-in), "
+                                                 "dense float32[N] to the host", "queries": ns,
+                                     "e2e": {"value": ns / dt, "unit": "queries/s"},
+                                     "kernel_ms_per_query": stats.phrase_kernel_ms / ns,
+                                     "mean_matching_docs": matched / ns}
+        if slop2_batch is not None:
+            phrase["slop2"] = slop2_batch
         # CPU side of the phrase workload: the oracle port, a few queries (each is 50-500 ms)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import search as osearch

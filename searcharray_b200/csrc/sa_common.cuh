@@ -118,6 +118,7 @@ struct sa_index {
     // host mirrors for query set-up
     std::vector<u64> h_off, h_len;
     std::vector<u32> h_df;
+    std::vector<unsigned char> h_first0;   // 1 = the term's first word sits at (doc 0, block 0): span-search corner
 
     // sliced-array filter (FilteredPosns semantics)
     u64 n_rows = 0;                  // number of selected rows

@@ -6,6 +6,7 @@
 
 #include "sa_term.cuh"
 #include "sa_phrase.cuh"
+#include "sa_span.cuh"
 
 // ------------------------------------------------------------------ error text
 static thread_local char g_err[1024] = "";
@@ -123,6 +124,9 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
     ix->h_len.assign(term_lengths, term_lengths + n_terms);
     ix->h_df.assign(n_terms, 0);
     ix->h_dir_off.assign(n_terms, SA_NO_DIR);
+    ix->h_first0.assign(n_terms, 0);
+    for (u32 t = 0; t < n_terms; t++)
+        if (term_lengths[t] && (words[term_offsets[t]] & SA_HDR_MASK) == 0) ix->h_first0[t] = 1;
 
 #define CREATE_CUDA(call)                                                              \
     do {                                                                               \
@@ -420,7 +424,7 @@ struct BatchChunk {
 };
 
 struct BatchState {
-    u32 nq = 0, k = 0, slots = 0, chunk = 0;
+    u32 nq = 0, k = 0, slots = 0, chunk = 0, slop = 0;
     float avg_doc_len = 0, k1 = 0, b = 0;
     bool ready = false;
     std::vector<TermQuery> tqs;               // all term queries, chunk by chunk
@@ -429,6 +433,10 @@ struct BatchState {
     std::vector<u32> term_query, phrase_query;  // index in tqs / pqs -> original query index
     std::vector<u32> phrase_missing;          // 1 = a term is unknown: result stays empty
     std::vector<BatchChunk> chunks;
+    // slop > 0: the multi-term queries are span queries (one plan per chunk, descriptors concatenated)
+    std::vector<SpanPlan> span_plans;
+    std::vector<float> span_idf;
+    DevBuf d_sq, d_scounts, d_sidf;
     DevBuf d_tq, d_pq, d_row_query;
     DevBuf d_meta;                            // u32 overflow[nq] (row space)
     DevBuf d_pstats;                          // PhraseStats[#phrase queries]
@@ -487,7 +495,6 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
                            float avg_doc_len, float k1, float b, uint32_t k) {
     SA_CHECK(ix && (n_queries == 0 || (terms && term_starts && idf)), "NULL argument");
     SA_CHECK(k >= 1 && k <= SA_TOPK_MAX, "k must be in [1, %d]", SA_TOPK_MAX);
-    SA_CHECK(slop == 0, "slop > 0 in a batch is not implemented yet");
     SA_CUDA(cudaSetDevice(ix->device));
     if (!ix->batch) ix->batch = new BatchState();
     BatchState &B = *ix->batch;
@@ -498,6 +505,8 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     B.avg_doc_len = avg_doc_len;
     B.k1 = k1;
     B.b = b;
+    B.slop = slop;
+    B.span_plans.clear(); B.span_idf.clear();
     B.tqs.clear(); B.pqs.clear(); B.row_query.clear(); B.term_query.clear(); B.phrase_query.clear();
     B.phrase_missing.clear(); B.chunks.clear();
     int rc;
@@ -508,6 +517,8 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     u32 chunk = (u32)std::max<u64>(1, std::min<u64>(n_queries, (4ull << 30) / (stride * sizeof(float))));
     B.chunk = std::min<u32>(chunk, 65535);
     u64 max_arena = 64;
+    size_t max_span_scratch = 0;
+    u32 n_span = 0;
     for (u32 q0 = 0; q0 < n_queries; q0 += B.chunk) {
         const u32 q1 = std::min(n_queries, q0 + B.chunk);
         BatchChunk C;
@@ -515,6 +526,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
         C.term0 = (u32)B.tqs.size();
         C.phrase0 = (u32)B.pqs.size();
         C.params = make_bm25(ix, 1.0f, avg_doc_len, k1, b);
+        SpanPlan plan;
         for (int pass = 0; pass < 2; pass++) {               // term queries first, then phrases
             for (u32 q = q0; q < q1; q++) {
                 const u32 nt = term_starts[q + 1] - term_starts[q];
@@ -528,6 +540,21 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
                 if (nt == 1) {
                     B.tqs.push_back(make_term_query(ix, tids[0], idf[q]));
                     B.term_query.push_back(q);
+                } else if (slop > 0) {
+                    // phrase with slop: span search (spans.py:171-187) on the index's own lists
+                    u64 offs[SA_MAX_PHRASE_TERMS], lens[SA_MAX_PHRASE_TERMS], dirs[SA_MAX_PHRASE_TERMS];
+                    bool missing = false, literal = true;
+                    for (u32 i = 0; i < nt; i++)
+                        if (tids[i] == SA_NO_TERM || ix->h_len[tids[i]] == 0) missing = true;
+                    for (u32 i = 0; i < nt; i++) {
+                        offs[i] = missing ? 0 : ix->h_off[tids[i]];
+                        lens[i] = missing ? 0 : ix->h_len[tids[i]];
+                        dirs[i] = missing ? SA_NO_DIR : ix->h_dir_off[tids[i]];
+                        literal = literal && !missing && ix->h_first0[tids[i]];
+                    }
+                    sa_span_plan_add(plan, offs, lens, dirs, nt, slop, idf[q], literal);
+                    B.span_idf.push_back(idf[q]);
+                    B.phrase_query.push_back(q);
                 } else {
                     PhraseQuery pq;
                     memset(&pq, 0, sizeof(pq));
@@ -548,6 +575,15 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
             }
         }
         C.n_term = (u32)B.tqs.size() - C.term0;
+        if (slop > 0) {
+            C.phrase0 = n_span;
+            C.n_phrase = (u32)plan.qs.size();
+            n_span += C.n_phrase;
+            max_span_scratch = std::max(max_span_scratch, sa_span_scratch_bytes(plan));
+            B.span_plans.push_back(std::move(plan));
+            B.chunks.push_back(C);
+            continue;
+        }
         C.n_phrase = (u32)B.pqs.size() - C.phrase0;
         if (C.n_phrase) {
             u64 want = std::max<u64>(1, (u64)ix->num_sms * 16 / C.n_phrase);
@@ -558,7 +594,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
         }
         B.chunks.push_back(C);
     }
-    SA_CHECK(B.chunks.empty() || B.chunks[0].params.sparse_ok || B.pqs.empty(),
+    SA_CHECK(B.chunks.empty() || B.chunks[0].params.sparse_ok || (B.pqs.empty() && n_span == 0),
              "phrase queries in a batch need ordinary BM25 parameters (k1 > 0, 0 <= b < 1, finite idf)");
     if ((rc = ix->dense.reserve((size_t)B.chunk * stride * sizeof(float)))) return rc;
     if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
@@ -568,6 +604,21 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     if ((rc = B.d_meta.reserve((size_t)n_queries * sizeof(u32)))) return rc;
     if ((rc = B.d_pstats.reserve(std::max<size_t>(B.pqs.size() * sizeof(PhraseStats), 64)))) return rc;
     if (!B.pqs.empty() && (rc = ix->phrase_scratch.reserve(max_arena * sizeof(u64) + 64))) return rc;
+    if (n_span) {
+        if ((rc = ix->phrase_scratch.reserve(max_span_scratch))) return rc;
+        if ((rc = B.d_sq.reserve((size_t)n_span * sizeof(SpanQuery)))) return rc;
+        if ((rc = B.d_scounts.reserve((size_t)n_span * sizeof(SpanCounts)))) return rc;
+        if ((rc = B.d_sidf.reserve((size_t)n_span * sizeof(float)))) return rc;
+        u32 at = 0;
+        for (const SpanPlan &pl : B.span_plans) {
+            if (pl.qs.empty()) continue;
+            SA_CUDA(cudaMemcpyAsync(B.d_sq.as<SpanQuery>() + at, pl.qs.data(), pl.qs.size() * sizeof(SpanQuery),
+                                    cudaMemcpyHostToDevice, ix->stream));
+            at += (u32)pl.qs.size();
+        }
+        SA_CUDA(cudaMemcpyAsync(B.d_sidf.p, B.span_idf.data(), (size_t)n_span * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        SA_CUDA(cudaStreamSynchronize(ix->stream));      // the plans' host vectors may be reallocated later
+    }
     if (!B.tqs.empty())
         SA_CUDA(cudaMemcpyAsync(B.d_tq.p, B.tqs.data(), B.tqs.size() * sizeof(TermQuery), cudaMemcpyHostToDevice, ix->stream));
     if (!B.pqs.empty())
@@ -593,6 +644,7 @@ int sa_batch_execute_locked(sa_index *ix) {
     if (!B.pqs.empty())
         SA_CUDA(cudaMemsetAsync(B.d_pstats.p, 0, B.pqs.size() * sizeof(PhraseStats), ix->stream));
     int rc;
+    size_t chunk_i = 0;
     for (const BatchChunk &C : B.chunks) {
         const u32 Q = C.n_term + C.n_phrase;
         TopkCtx t = make_topk_ctx(ix, Q, B.slots, B.k, d_ovf + C.row0);
@@ -600,7 +652,18 @@ int sa_batch_execute_locked(sa_index *ix) {
             TermBatchArgs a = make_term_args(ix, B.d_tq.as<TermQuery>() + C.term0, C.params, t);
             if ((rc = launch_term_batch(ix, a, C.n_term))) return rc;
         }
-        if (C.n_phrase) {
+        if (B.slop > 0) {
+            const SpanPlan &plan = B.span_plans[chunk_i++];
+            if (C.n_phrase) {
+                // span counts into zeroed rows, then one tile pass scores them in place and collects top-k
+                float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;
+                if ((rc = sa_ensure_norm(ix, B.k1, B.b, B.avg_doc_len))) return rc;
+                if ((rc = sa_span_enqueue(ix, ix->d_words, plan, B.d_sq.as<SpanQuery>() + C.phrase0,
+                                          B.d_scounts.as<SpanCounts>() + C.phrase0, ix->phrase_scratch.p, rows, stride))) return rc;
+                if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, C.n_term, C.n_phrase, t,
+                                                  B.d_sidf.as<float>() + C.phrase0))) return rc;
+            }
+        } else if (C.n_phrase) {
             float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;
             unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
             SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
@@ -616,7 +679,7 @@ int sa_batch_execute_locked(sa_index *ix) {
 
 // Re-run one query exactly (synchronously): a tile overflowed its candidate slots, or a phrase's
 // same-term speculation was wrong.  Uses a slot per doc of the tile -- cannot overflow.
-static int redo_query(sa_index *ix, BatchState &B, bool is_phrase, u32 idx, u32 q) {
+static int redo_query(sa_index *ix, BatchState &B, bool is_phrase, u32 idx, u32 q, const SpanQuery *sq = nullptr) {
     int rc;
     const u64 stride = padded_docs(ix->n_docs);
     if ((rc = ix->cand.reserve(cand_bytes(ix, 1, SA_TILE_DOCS)))) return rc;
@@ -626,6 +689,11 @@ static int redo_query(sa_index *ix, BatchState &B, bool is_phrase, u32 idx, u32 
         Bm25Params p = make_bm25(ix, B.tqs[idx].idf, B.avg_doc_len, B.k1, B.b);
         TermBatchArgs a = make_term_args(ix, B.d_tq.as<TermQuery>() + idx, p, t);
         if ((rc = launch_term_batch(ix, a, 1))) return rc;
+    } else if (sq) {
+        if ((rc = sa_ensure_norm(ix, B.k1, B.b, B.avg_doc_len))) return rc;
+        if ((rc = sa_span_run(ix, ix->d_words, sq->off, sq->len, sq->dir_off, sq->n_terms, sq->slop, sq->literal != 0, nullptr))) return rc;
+        SA_CUDA(cudaMemcpyAsync(B.d_sidf.p, &sq->idf, sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+        if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, 0, 1, t, B.d_sidf.as<float>()))) return rc;
     } else {
         Bm25Params p = make_bm25(ix, B.pqs[idx].idf, B.avg_doc_len, B.k1, B.b);
         std::vector<PhraseQuery> one(1, B.pqs[idx]);
@@ -633,7 +701,7 @@ static int redo_query(sa_index *ix, BatchState &B, bool is_phrase, u32 idx, u32 
         memset(&nodump, 0, sizeof(nodump));
         if ((rc = sa_phrase_run_sync(ix, one, ix->d_words, 1, p, 0, nodump))) return rc;   // loops until the guess holds
         B.pqs[idx] = one[0];
-        if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, 0, 1, t))) return rc;
+        if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, 0, 1, t, nullptr))) return rc;
     }
     SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, &q, sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
     if ((rc = launch_topk_select(ix, t, 1, ix->doc_base, ix->topk_out.as<u64>(), B.d_row_query.as<u32>()))) return rc;
@@ -656,27 +724,41 @@ int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
     std::vector<u32> ovf((const u32 *)ix->h_pinned, (const u32 *)ix->h_pinned + B.nq);       // row space
     std::vector<PhraseStats> st(B.pqs.size());
     if (st_bytes) memcpy(st.data(), (char *)ix->h_pinned + ovf_bytes, st_bytes);
-    struct Redo { bool phrase; u32 idx, q; };
+    struct Redo { bool phrase; u32 idx, q; const SpanQuery *sq; };
     std::vector<Redo> redo;
+    size_t chunk_i = 0;
     for (const BatchChunk &C : B.chunks) {
         for (u32 i = 0; i < C.n_term; i++)
-            if (ovf[C.row0 + i]) redo.push_back({false, C.term0 + i, B.term_query[C.term0 + i]});
+            if (ovf[C.row0 + i]) redo.push_back({false, C.term0 + i, B.term_query[C.term0 + i], nullptr});
+        if (B.slop > 0) {
+            const SpanPlan &plan = B.span_plans[chunk_i++];
+            for (u32 i = 0; i < C.n_phrase; i++)
+                if (ovf[C.row0 + C.n_term + i])
+                    redo.push_back({true, C.phrase0 + i, B.phrase_query[C.phrase0 + i], &plan.qs[i]});
+            continue;
+        }
         for (u32 i = 0; i < C.n_phrase; i++) {
             const u32 pi = C.phrase0 + i;
             SA_CHECK(!st[pi].overflow, "phrase scratch arena exhausted (internal sizing error)");
             PhraseQuery trial = B.pqs[pi];
             bool ok = B.phrase_missing[pi] || sa_phrase_guess_ok(trial, st[pi]);
-            if (!ok || ovf[C.row0 + C.n_term + i]) redo.push_back({true, pi, B.phrase_query[pi]});
+            if (!ok || ovf[C.row0 + C.n_term + i]) redo.push_back({true, pi, B.phrase_query[pi], nullptr});
         }
     }
     if (redo.empty()) return SA_OK;
     for (const Redo &r : redo)
-        if ((rc = redo_query(ix, B, r.phrase, r.idx, r.q))) return rc;
+        if ((rc = redo_query(ix, B, r.phrase, r.idx, r.q, r.sq))) return rc;
     // the repair buffers are larger than the batch's: restore the normal ones and descriptors
     if ((rc = ix->cand.reserve(cand_bytes(ix, B.chunk, B.slots)))) return rc;
     SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, B.row_query.data(), (size_t)B.nq * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
     if (!B.pqs.empty())
         SA_CUDA(cudaMemcpyAsync(B.d_pq.p, B.pqs.data(), B.pqs.size() * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
+    if (!B.span_idf.empty()) {
+        size_t need = 0;
+        for (const SpanPlan &pl : B.span_plans) need = std::max(need, sa_span_scratch_bytes(pl));
+        if ((rc = ix->phrase_scratch.reserve(need))) return rc;
+        SA_CUDA(cudaMemcpyAsync(B.d_sidf.p, B.span_idf.data(), B.span_idf.size() * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    }
     SA_CUDA(cudaStreamSynchronize(ix->stream));
     if (n_redone) *n_redone = (u32)redo.size();
     return SA_OK;
@@ -805,6 +887,9 @@ void sa_free_batch(sa_index *ix) {
     ix->batch->d_row_query.release();
     ix->batch->d_meta.release();
     ix->batch->d_pstats.release();
+    ix->batch->d_sq.release();
+    ix->batch->d_scounts.release();
+    ix->batch->d_sidf.release();
     delete ix->batch;
     ix->batch = nullptr;
 }

@@ -26,10 +26,9 @@
 #include <algorithm>
 
 #include "sa_phrase.cuh"
+#include "sa_span.cuh"
 #include "sa_term.cuh"
 
-int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, uint32_t n_terms, uint32_t slop,
-                u32 *n_undefined);
 int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bool use_rows,
                     u64 pay_lo, u64 pay_hi, bool use_payload, std::vector<u64> &offs, std::vector<u64> &lens);
 int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
@@ -729,7 +728,17 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
     }
     if (!missing && slop > 0) {
         // span search (phrase/spans.py + roaringish/spans.pyx): raw counts, BM25 afterwards
-        if ((rc = sa_span_run(ix, d_lists, offs.data(), lens.data(), n_terms, slop, nullptr))) return rc;
+        std::vector<u64> dirs(n_terms, SA_NO_DIR);
+        bool literal = true;
+        if (d_lists == ix->d_words) {
+            for (u32 i = 0; i < n_terms; i++) {
+                dirs[i] = ix->h_dir_off[term_ids[i]];
+                literal = literal && ix->h_first0[term_ids[i]];
+            }
+        } else if ((rc = sa_span_is_literal(ix, d_lists, offs.data(), lens.data(), n_terms, &literal))) {
+            return rc;
+        }
+        if ((rc = sa_span_run(ix, d_lists, offs.data(), lens.data(), dirs.data(), n_terms, slop, literal, nullptr))) return rc;
         raw_counts = score != 0;
     } else if (!missing) {
         std::vector<PhraseQuery> pqs(1);

@@ -4,15 +4,22 @@
 //   span_search / _intersect_all            searcharray/phrase/spans.py:71-187
 //   _span_freqs, _compact_spans, _collect_spans, ActiveSpans   searcharray/roaringish/spans.pyx:70-319
 //
-// Phase 1 (span_candidates_kernel, one CTA per query) restates _intersect_all as a membership test.
-// With A = headers of term 0 and B_k = headers of term k (header = doc|block), the reference keeps,
-// for every term, the words whose header lies in  H = L u R u (L - 1) u (R + 1)  where
+// Phase 1 restates _intersect_all as a membership test.  With A = headers of term 0 and B_k = headers
+// of term k (header = doc|block), the reference keeps, for every term, the words whose header lies in
+//   H = L u R u (L - 1) u (R + 1)  where
 //   L = AND_k [ (A(x)&B_k(x)) | (B_k(x)&A(x-1)) | (A(x)&B_k(x-1)) ]
 //   R = AND_k [ (A(x)&B_k(x)) | (A(x)&B_k(x+1)) | (B_k(x)&A(x+1)) ]
 // (the merges / intersects / adjacents of spans.py:79-112 reduce to these presence tests because
 // they are applied with the header mask and set semantics).  Every x in H has each term within two
 // blocks, so the candidates are enumerated, already sorted and unique, from the shortest list:
 // word s (header hs) emits hs-2..hs+2, each only if no earlier word of that list covers it.
+//   span_presence_kernel  one thread per generator word (grid = generator CTAs x queries): ONE
+//                         search per term (narrowed by the term's tile directory) gives the presence
+//                         of headers hs-3..hs+3; the five candidates are evaluated from those bits.
+//                         Kept words are counted per (term, CTA) together with their doc-group starts.
+//   span_scan_kernel      per query: exclusive scans over the generator CTAs (word offsets, group
+//                         offsets; a group that continues across a CTA boundary is not a new start).
+//   span_write_kernel     writes every term's sliced list and its doc-group starts, in order.
 // Phase 2 (span_groups_kernel) replays _span_freqs.  The reference walks all terms "up to the next
 // doc change" in lock step, i.e. iteration i consumes the i-th DOC GROUP of every term's sliced list
 // (normally the same doc; the lists can be misaligned, and then this pairing is what defines the
@@ -21,50 +28,51 @@
 // ballots.  Counts are accumulated per `last_key` like the reference's Counter.
 #include <algorithm>
 
-#include "sa_phrase.cuh"
+#include "sa_span.cuh"
 #include "sa_term.cuh"
 
 #define SPAN_CAP 512
 #define SPAN_WARPS 4
-#define CAND_THREADS 256
+#define GEN_THREADS 256
 
-struct SpanQuery {
-    u32 n_terms;
-    u32 slop;
-    u32 shortest;                       // index of the shortest list (candidate generator)
-    u32 pad;
-    u64 off[SA_MAX_PHRASE_TERMS];       // term lists in d_words
-    u64 len[SA_MAX_PHRASE_TERMS];
-    u64 s_off[SA_MAX_PHRASE_TERMS];     // sliced-list region of term t in the word arena
-    u64 g_off[SA_MAX_PHRASE_TERMS];     // group-start region of term t in the u32 arena
-    u64 s_cap[SA_MAX_PHRASE_TERMS];
-};
-
-struct SpanCounts {                      // written by phase 1, read by phase 2
-    u32 n_sliced[SA_MAX_PHRASE_TERMS];
-    u32 n_groups[SA_MAX_PHRASE_TERMS];
-    u32 overflow;
-    u32 undefined;                       // span-table overflows the reference leaves undefined
+struct CtaRec {                          // per (query, term, generator CTA)
+    u32 count;                           // kept words            -> after the scan: word offset
+    u32 starts;                          // doc-group starts      -> after the scan: group offset
+    u32 first_p1;                        // doc + 1 of the first kept word (0 = none) -> after the scan: 1 = first word continues a group
+    u32 last_p1;                         // doc + 1 of the last kept word
 };
 
 struct SpanArgs {
     const u64 *words;
+    const u32 *tile_dir;
     const SpanQuery *queries;
     SpanCounts *counts;
     u64 *word_arena;
     u32 *group_arena;
+    u64 *rec;                            // p | mask7 << 32 | put5 << 39 | start5 << 44
+    u32 *rec2;                           // local word offset | local start rank << 16
+    CtaRec *cta;
     float *out;                          // [Q][out_stride] pre-zeroed: out[last_key - doc_base] += count
     u64 out_stride;
     u64 n_docs, doc_base;
 };
 
-__device__ __forceinline__ u64 lb_hdr(const u64 *__restrict__ a, u64 n, u64 target) {
-    u64 lo = 0, hi = n;
-    while (lo < hi) {
-        u64 mid = (lo + hi) >> 1;
-        if ((a[mid] & SA_HDR_MASK) < target) lo = mid + 1; else hi = mid;
+// first index in [0, len) whose header is >= target
+__device__ __forceinline__ u32 lb_hdr(const u64 *__restrict__ a, u64 len, const u32 *__restrict__ dir,
+                                      u64 target, u64 doc_base) {
+    u64 lo = 0, hi = len;
+    if (dir) {
+        const u64 doc = target >> SA_KEY_SHIFT;
+        if (doc < doc_base) return 0;                       // below the shard: every word is >= target
+        const u64 tile = (doc - doc_base) / SA_TILE_DOCS;
+        lo = __ldg(dir + tile);
+        hi = __ldg(dir + tile + 1);
     }
-    return lo;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if ((__ldg(a + mid) & SA_HDR_MASK) < target) lo = mid + 1; else hi = mid;
+    }
+    return (u32)lo;
 }
 
 __device__ __forceinline__ u32 block_scan_excl(u32 v, u32 *warp_sums, u32 &total) {
@@ -79,7 +87,8 @@ __device__ __forceinline__ u32 block_scan_excl(u32 v, u32 *warp_sums, u32 &total
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     u32 base = 0, tot = 0;
-    for (int w = 0; w < CAND_THREADS / 32; w++) {
+#pragma unroll
+    for (int w = 0; w < GEN_THREADS / 32; w++) {
         u32 s = warp_sums[w];
         if (w < (int)warp) base += s;
         tot += s;
@@ -88,96 +97,221 @@ __device__ __forceinline__ u32 block_scan_excl(u32 v, u32 *warp_sums, u32 &total
     return base + incl - v;
 }
 
+// exclusive running maximum (0 = nothing before); `total` = maximum over the block
+__device__ __forceinline__ u32 block_scan_excl_max(u32 v, u32 *warp_max, u32 &total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = max(incl, t);
+    }
+    u32 excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0;
+    __syncthreads();
+    if (lane == 31) warp_max[warp] = incl;
+    __syncthreads();
+    u32 base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < GEN_THREADS / 32; w++) {
+        u32 s = warp_max[w];
+        if (w < (int)warp) base = max(base, s);
+        tot = max(tot, s);
+    }
+    total = tot;
+    return max(base, excl);
+}
+
 // ---------------------------------------------------------------------------- phase 1
-__global__ void __launch_bounds__(CAND_THREADS)
-span_candidates_kernel(const SpanArgs a) {
-    __shared__ u32 s_warp[CAND_THREADS / 32];
-    __shared__ u32 s_count[SA_MAX_PHRASE_TERMS];
-    __shared__ u32 s_last_doc[SA_MAX_PHRASE_TERMS], s_groups[SA_MAX_PHRASE_TERMS];
-    const u32 q = blockIdx.x;
+__global__ void __launch_bounds__(GEN_THREADS)
+span_presence_kernel(const SpanArgs a) {
+    __shared__ u32 s_warp[GEN_THREADS / 32];
+    __shared__ u32 s_first;
+    const u32 q = blockIdx.y;
     const SpanQuery &sq = a.queries[q];
+    if (sq.literal || blockIdx.x >= sq.n_ctas) return;                 // CTA-uniform
     const u32 n = sq.n_terms;
     const unsigned tid = threadIdx.x;
-    if (tid < SA_MAX_PHRASE_TERMS) { s_count[tid] = 0; s_groups[tid] = 0; s_last_doc[tid] = 0xFFFFFFFFu; }
-    __syncthreads();
-    const u64 *S = a.words + sq.off[sq.shortest];
+    const u64 *__restrict__ S = a.words + sq.off[sq.shortest];
     const u64 nS = sq.len[sq.shortest];
-    constexpr u32 PER = CAND_THREADS / 5;                 // 51 generator words per pass, 5 candidates each
+    const u64 si = (u64)blockIdx.x * GEN_THREADS + tid;
+    const bool active = si < nS;
+    u64 hs = 0, hp = 0;
+    if (active) {
+        hs = __ldg(S + si) & SA_HDR_MASK;
+        if (si > 0) hp = __ldg(S + si - 1) & SA_HDR_MASK;
+    }
+    u64 *__restrict__ rec = a.rec + sq.rec_off + si * n;
+    u32 *__restrict__ rec2 = a.rec2 + sq.rec_off + si * n;
 
-    for (u64 base = 0; base < nS; base += PER) {          // CTA-uniform
-        const u32 j = tid / 5;
-        const int delta = (int)(tid % 5) - 2;
-        const u64 si = base + j;
-        bool cand = (tid < PER * 5) && si < nS;
-        u64 x = 0;
-        if (cand) {
-            const u64 hs = S[si] & SA_HDR_MASK;
-            if (delta < 0 && hs < (u64)(-delta) * SA_ONE_BLOCK) cand = false;
-            else x = hs + (u64)((i64)delta * (i64)SA_ONE_BLOCK);
-            // emitted by the FIRST generator word within two blocks of x
-            if (cand && si > 0) {
-                const u64 hp = S[si - 1] & SA_HDR_MASK;
-                if (hp + 2 * SA_ONE_BLOCK >= x) cand = false;
+    // A. presence of every term at hs-3 .. hs+3 (bit o <-> header hs + (o-3) blocks)
+    u64 mm[2] = {0, 0};                                                 // 8 bits per term
+    if (active) {
+        const u64 target = hs >= 3 * SA_ONE_BLOCK ? hs - 3 * SA_ONE_BLOCK : 0;
+        const u64 top = hs + 3 * SA_ONE_BLOCK;
+        for (u32 t = 0; t < n; t++) {
+            const u64 *__restrict__ lst = a.words + sq.off[t];
+            const u64 len = sq.len[t];
+            const u32 *dir = (sq.dir_off[t] != SA_NO_DIR && a.tile_dir) ? a.tile_dir + sq.dir_off[t] : nullptr;
+            const u32 p = lb_hdr(lst, len, dir, target, a.doc_base);
+            u32 m7 = 0;
+            for (u32 r = 0; r < 7 && (u64)p + r < len; r++) {
+                const u64 h = __ldg(lst + p + r) & SA_HDR_MASK;
+                if (h > top) break;
+                const int o = (int)((i64)(h - hs) >> SA_LSB_BITS) + 3;   // headers are multiples of one block
+                m7 |= 1u << o;
             }
+            rec[t] = (u64)p | ((u64)m7 << 32);
+            if (t < 8) mm[0] |= (u64)m7 << (8 * t); else mm[1] |= (u64)m7 << (8 * (t - 8));
         }
-        // presence of every term at x-1, x, x+1 (bit 0: x-1, bit 1: x, bit 2: x+1)
-        u32 pres[SA_MAX_PHRASE_TERMS];
-        u64 at_x[SA_MAX_PHRASE_TERMS];
-        bool keep = false;
-        if (cand) {
-            const bool has_m1 = x >= SA_ONE_BLOCK;
-            for (u32 t = 0; t < n; t++) {
-                const u64 *lst = a.words + sq.off[t];
-                const u64 len = sq.len[t];
-                u64 p = lb_hdr(lst, len, has_m1 ? x - SA_ONE_BLOCK : x);
-                u32 m = 0;
-                at_x[t] = 0;
-                for (int r = 0; r < 3 && p < len; r++) {
-                    const u64 w = lst[p];
-                    const u64 h = w & SA_HDR_MASK;
-                    if (has_m1 && h == x - SA_ONE_BLOCK) { m |= 1u; p++; }
-                    else if (h == x) { m |= 2u; at_x[t] = w; p++; }
-                    else if (h == x + SA_ONE_BLOCK) { m |= 4u; p++; }
-                    else break;
-                }
-                pres[t] = m;
-            }
-            // L(y), R(y) for y in {x-1, x, x+1} as far as the presence window allows
-            auto A = [&](int o) { return (pres[0] >> (o + 1)) & 1u; };       // o in {-1,0,1}
-            bool Lx = true, Rx = true, Lx1 = true, Rxm1 = true;
+    }
+    auto m7_of = [&](u32 t) -> u32 { return (u32)(((t < 8) ? (mm[0] >> (8 * t)) : (mm[1] >> (8 * (t - 8)))) & 0x7Fu); };
+
+    // B. the five candidates x = hs + d blocks, d = -2..2 (bit d+2 of keep5)
+    u32 keep5 = 0;
+    if (active) {
+        for (int d = -2; d <= 2; d++) {
+            if (d < 0 && hs < (u64)(-d) * SA_ONE_BLOCK) continue;
+            const u64 x = hs + (u64)((i64)d * (i64)SA_ONE_BLOCK);
+            // emitted by the FIRST generator word within two blocks of x
+            if (si > 0 && hp + 2 * SA_ONE_BLOCK >= x) continue;
+            // presence at x-1, x, x+1 = bits d+2, d+3, d+4
+            const u32 pa = (m7_of(0) >> (d + 2)) & 7u;
+            auto A = [&](int o) { return (pa >> (o + 1)) & 1u; };       // o in {-1,0,1}
+            u32 Lx = 1, Rx = 1, Lx1 = 1, Rxm1 = 1;
             for (u32 k = 1; k < n; k++) {
-                auto Bk = [&](int o) { return (pres[k] >> (o + 1)) & 1u; };
+                const u32 pb = (m7_of(k) >> (d + 2)) & 7u;
+                auto Bk = [&](int o) { return (pb >> (o + 1)) & 1u; };
                 Lx &= (A(0) & Bk(0)) | (Bk(0) & A(-1)) | (A(0) & Bk(-1));
                 Rx &= (A(0) & Bk(0)) | (A(0) & Bk(1)) | (Bk(0) & A(1));
                 Lx1 &= (A(1) & Bk(1)) | (Bk(1) & A(0)) | (A(1) & Bk(0));          // L(x+1)
                 Rxm1 &= (A(-1) & Bk(-1)) | (A(-1) & Bk(0)) | (Bk(-1) & A(0));      // R(x-1)
             }
-            keep = Lx | Rx | Lx1 | Rxm1;
-        }
-        // ordered append of the kept words, term by term
-        for (u32 t = 0; t < n; t++) {
-            const bool put = keep && (pres[t] & 2u);
-            u32 total;
-            u32 off = block_scan_excl(put ? 1u : 0u, s_warp, total);
-            const u32 cnt0 = s_count[t];
-            if (put) {
-                if (cnt0 + off < sq.s_cap[t]) a.word_arena[sq.s_off[t] + cnt0 + off] = at_x[t];
-                else a.counts[q].overflow = 1;
-            }
-            __syncthreads();
-            if (tid == 0) s_count[t] = cnt0 + total;
-            __syncthreads();
+            if (Lx | Rx | Lx1 | Rxm1) keep5 |= 1u << (d + 2);
         }
     }
-    if (tid < n) a.counts[q].n_sliced[tid] = min(s_count[tid], (u32)sq.s_cap[tid]);
+
+    // C. per term: which candidates hold a word of the term, where its doc groups start, and this
+    //    thread's offsets inside the CTA
+    for (u32 t = 0; t < n; t++) {                                       // CTA-uniform
+        const u32 put5 = active ? (keep5 & (m7_of(t) >> 1) & 0x1Fu) : 0u;
+        const u32 cnt = __popc(put5);
+        u32 first_p1 = 0, last_p1 = 0;
+        if (cnt) {
+            const int d_lo = __ffs(put5) - 3, d_hi = (31 - __clz(put5)) - 2;
+            first_p1 = (u32)((hs + (u64)((i64)d_lo * (i64)SA_ONE_BLOCK)) >> SA_KEY_SHIFT) + 1;
+            last_p1 = (u32)((hs + (u64)((i64)d_hi * (i64)SA_ONE_BLOCK)) >> SA_KEY_SHIFT) + 1;
+        }
+        u32 cta_last;
+        u32 prev_p1 = block_scan_excl_max(last_p1, s_warp, cta_last);   // docs ascend: max = most recent
+        u32 start5 = 0;
+        for (int d = -2; d <= 2; d++) {
+            if (!((put5 >> (d + 2)) & 1u)) continue;
+            const u32 doc_p1 = (u32)((hs + (u64)((i64)d * (i64)SA_ONE_BLOCK)) >> SA_KEY_SHIFT) + 1;
+            if (doc_p1 != prev_p1) start5 |= 1u << (d + 2);
+            prev_p1 = doc_p1;
+        }
+        u32 total;
+        const u32 off = block_scan_excl(cnt | ((u32)__popc(start5) << 16), s_warp, total);
+        if (tid == 0) s_first = 0;
+        __syncthreads();
+        if (cnt && (off & 0xFFFFu) == 0) s_first = first_p1;            // the CTA's first kept word
+        if (active) {
+            rec[t] |= ((u64)put5 << 39) | ((u64)start5 << 44);
+            rec2[t] = off;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            CtaRec r;
+            r.count = total & 0xFFFFu;
+            r.starts = total >> 16;
+            r.first_p1 = s_first;
+            r.last_p1 = cta_last;
+            a.cta[sq.cta_off + (u64)t * sq.n_ctas + blockIdx.x] = r;
+        }
+        __syncthreads();
+    }
 }
 
-// doc groups of every sliced list (runs after either candidate kernel)
-__global__ void __launch_bounds__(CAND_THREADS)
-span_groups_build_kernel(const SpanArgs a) {
-    __shared__ u32 s_warp[CAND_THREADS / 32];
-    __shared__ u32 s_groups;
+// exclusive scans over the generator CTAs of every term of one query
+__global__ void __launch_bounds__(GEN_THREADS)
+span_scan_kernel(const SpanArgs a) {
+    __shared__ u32 s_warp[GEN_THREADS / 32];
     const u32 q = blockIdx.x;
+    const SpanQuery &sq = a.queries[q];
+    if (sq.literal) return;
+    const unsigned tid = threadIdx.x;
+    for (u32 t = 0; t < sq.n_terms; t++) {
+        CtaRec *__restrict__ recs = a.cta + sq.cta_off + (u64)t * sq.n_ctas;
+        u32 carry_w = 0, carry_g = 0, carry_last = 0;
+        for (u32 base = 0; base < sq.n_ctas; base += GEN_THREADS) {
+            const u32 c = base + tid;
+            CtaRec r = {0, 0, 0, 0};
+            if (c < sq.n_ctas) r = recs[c];
+            u32 blk_last, tot_w, tot_g;
+            const u32 prev_last = max(block_scan_excl_max(r.last_p1, s_warp, blk_last), carry_last);
+            const u32 adj = (r.count && r.first_p1 == prev_last) ? 1u : 0u;
+            const u32 w_off = block_scan_excl(r.count, s_warp, tot_w) + carry_w;
+            const u32 g_off = block_scan_excl(r.starts - adj, s_warp, tot_g) + carry_g;
+            if (c < sq.n_ctas) {
+                r.count = w_off; r.starts = g_off; r.first_p1 = adj;
+                recs[c] = r;
+            }
+            carry_w += tot_w;
+            carry_g += tot_g;
+            carry_last = max(carry_last, blk_last);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (carry_w > sq.s_cap[t]) a.counts[q].overflow = 1;
+            a.counts[q].n_sliced[t] = carry_w;
+            a.counts[q].n_groups[t] = carry_g;
+            a.group_arena[sq.g_off[t] + carry_g] = carry_w;              // sentinel: end of the last group
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GEN_THREADS)
+span_write_kernel(const SpanArgs a) {
+    const u32 q = blockIdx.y;
+    const SpanQuery &sq = a.queries[q];
+    if (sq.literal || blockIdx.x >= sq.n_ctas || a.counts[q].overflow) return;
+    const u32 n = sq.n_terms;
+    const u64 si = (u64)blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (si >= sq.len[sq.shortest]) return;
+    const u64 *__restrict__ rec = a.rec + sq.rec_off + si * n;
+    const u32 *__restrict__ rec2 = a.rec2 + sq.rec_off + si * n;
+    for (u32 t = 0; t < n; t++) {
+        const u64 r = rec[t];
+        const u32 put5 = (u32)(r >> 39) & 0x1Fu;
+        if (!put5) continue;
+        const u32 start5 = (u32)(r >> 44) & 0x1Fu, m7 = (u32)(r >> 32) & 0x7Fu, p = (u32)r;
+        const u32 r2 = rec2[t];
+        const CtaRec c = a.cta[sq.cta_off + (u64)t * sq.n_ctas + blockIdx.x];
+        u32 pos = c.count + (r2 & 0xFFFFu);
+        u32 rank = r2 >> 16;
+        const u64 *__restrict__ lst = a.words + sq.off[t];
+        u64 *__restrict__ sl = a.word_arena + sq.s_off[t];
+        u32 *__restrict__ gs = a.group_arena + sq.g_off[t];
+        for (int b = 0; b < 5; b++) {
+            if (!((put5 >> b) & 1u)) continue;
+            const u32 widx = p + __popc(m7 & ((1u << (b + 1)) - 1u));   // header hs + (b-2) blocks <-> bit b+1
+            sl[pos] = __ldg(lst + widx);
+            if ((start5 >> b) & 1u) {
+                // the CTA's first kept word continues the previous CTA's doc group when c.first_p1 == 1
+                if (!(rank == 0 && c.first_p1)) gs[c.starts + rank - c.first_p1] = pos;
+                rank++;
+            }
+            pos++;
+        }
+    }
+}
+
+// doc groups of every sliced list, single CTA (used after the literal candidate kernel)
+__global__ void __launch_bounds__(GEN_THREADS)
+span_groups_build_kernel(const SpanArgs a, u32 q) {
+    __shared__ u32 s_warp[GEN_THREADS / 32];
+    __shared__ u32 s_groups;
     const SpanQuery &sq = a.queries[q];
     const unsigned tid = threadIdx.x;
     for (u32 t = 0; t < sq.n_terms; t++) {
@@ -185,7 +319,7 @@ span_groups_build_kernel(const SpanArgs a) {
         const u64 *sl = a.word_arena + sq.s_off[t];
         if (tid == 0) s_groups = 0;
         __syncthreads();
-        for (u32 base = 0; base < cnt; base += CAND_THREADS) {
+        for (u32 base = 0; base < cnt; base += GEN_THREADS) {
             const u32 i = base + tid;
             bool start = false;
             if (i < cnt) start = (i == 0) || ((sl[i] >> SA_KEY_SHIFT) != (sl[i - 1] >> SA_KEY_SHIFT));
@@ -291,9 +425,9 @@ __device__ u64 dev_intersect_keep_rhs(const u64 *lhs, u64 nl, const u64 *rhs, u6
     return m;
 }
 
-__global__ void span_candidates_literal_kernel(const SpanArgs a, u64 *scratch, u64 cap3 /* 3*|A| + 8 */) {
+__global__ void span_candidates_literal_kernel(const SpanArgs a, u32 q, u64 *scratch, u64 cap3 /* 3*|A| + 8 */) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const SpanQuery &sq = a.queries[0];
+    const SpanQuery &sq = a.queries[q];
     const u32 n = sq.n_terms;
     const u64 M = SA_HDR_MASK;
     u64 *lh = scratch, *rh = lh + cap3, *tmp = rh + cap3, *tmp2 = tmp + cap3;
@@ -341,7 +475,7 @@ __global__ void span_candidates_literal_kernel(const SpanArgs a, u64 *scratch, u
     for (u64 j = 0; j < na; j++) allh[j] &= M;
     for (u32 t = 0; t < n; t++) {
         u64 m = dev_intersect_keep_rhs(allh, na, a.words + sq.off[t], sq.len[t], M, a.word_arena + sq.s_off[t]);
-        a.counts[0].n_sliced[t] = (u32)m;
+        a.counts[q].n_sliced[t] = (u32)m;
     }
 }
 
@@ -419,14 +553,15 @@ __device__ u32 collect_spans(WarpSpans &S, u32 cursor, u32 n_terms, int max_w) {
 }
 
 __global__ void __launch_bounds__(SPAN_WARPS * 32)
-span_groups_kernel(const SpanArgs a, u32 n_queries) {
+span_groups_kernel(const SpanArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSpans &S = reinterpret_cast<WarpSpans *>(smem_raw)[warp];
     const u32 warps_total = gridDim.x * SPAN_WARPS;
     const u32 warp_global = blockIdx.x * SPAN_WARPS + warp;
 
-    for (u32 q = 0; q < n_queries; q++) {
+    {
+        const u32 q = blockIdx.y;
         const SpanQuery &sq = a.queries[q];
         const SpanCounts &sc = a.counts[q];
         const u32 n = sq.n_terms;
@@ -531,82 +666,154 @@ span_groups_kernel(const SpanArgs a, u32 n_queries) {
 
 // --------------------------------------------------------------------------------- host
 static u64 padded_stride(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * SA_TILE_DOCS; }
+static u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
 
-// Span search of one query into ix->dense row 0 (raw counts).  Caller holds ix->mu.
-int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, uint32_t n_terms, uint32_t slop,
-                u32 *n_undefined) {
-    const u64 stride = padded_stride(ix->n_docs);
-    int rc;
-    if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
-    SA_CUDA(cudaMemsetAsync(ix->dense.p, 0, stride * sizeof(float), ix->stream));
+void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u64 *dir_offs, u32 n_terms,
+                      u32 slop, float idf, bool literal) {
     SpanQuery sq;
     memset(&sq, 0, sizeof(sq));
     sq.n_terms = n_terms;
     sq.slop = slop;
+    sq.idf = idf;
+    sq.literal = literal ? 1u : 0u;
     u64 shortest_len = ~0ull;
     for (u32 t = 0; t < n_terms; t++) {
         sq.off[t] = offs[t];
         sq.len[t] = lens[t];
+        sq.dir_off[t] = dir_offs ? dir_offs[t] : SA_NO_DIR;
         if (sq.len[t] < shortest_len) { shortest_len = sq.len[t]; sq.shortest = t; }
     }
-    u64 words_total = 0, groups_total = 0;
+    if (n_terms == 0) shortest_len = 0;
     for (u32 t = 0; t < n_terms; t++) {
         sq.s_cap[t] = std::min<u64>(sq.len[t], 5 * shortest_len);
-        sq.s_off[t] = words_total;
-        sq.g_off[t] = groups_total;
-        words_total += sq.s_cap[t] + 2;
-        groups_total += sq.s_cap[t] + 2;
+        sq.s_off[t] = plan.words_total;
+        sq.g_off[t] = plan.groups_total;
+        plan.words_total += sq.s_cap[t] + 2;
+        plan.groups_total += sq.s_cap[t] + 2;
     }
-    SA_CHECK(groups_total < 0xFFFFFFFFull, "slop query too large");
-    if ((rc = ix->phrase_scratch.reserve(words_total * sizeof(u64) + groups_total * sizeof(u32) + 256))) return rc;
-    if ((rc = ix->queries.reserve(sizeof(SpanQuery)))) return rc;
-    if ((rc = ix->cand_meta.reserve(sizeof(SpanCounts)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->queries.p, &sq, sizeof(sq), cudaMemcpyHostToDevice, ix->stream));
-    SA_CUDA(cudaMemsetAsync(ix->cand_meta.p, 0, sizeof(SpanCounts), ix->stream));
+    sq.n_ctas = literal ? 0u : (u32)((shortest_len + GEN_THREADS - 1) / GEN_THREADS);
+    sq.rec_off = plan.rec_total;
+    sq.cta_off = plan.cta_total;
+    if (!literal) {
+        plan.rec_total += shortest_len * n_terms;
+        plan.cta_total += (u64)sq.n_ctas * n_terms;
+    }
+    plan.max_ctas = std::max(plan.max_ctas, sq.n_ctas);
+    plan.max_shortest = std::max(plan.max_shortest, shortest_len);
+    plan.any_literal |= literal;
+    plan.qs.push_back(sq);
+}
+
+struct SpanLayout { u64 words, groups, rec, rec2, cta, total; };
+static SpanLayout span_layout(const SpanPlan &plan) {
+    SpanLayout L;
+    L.words = 0;
+    L.groups = align_up(L.words + plan.words_total * sizeof(u64), 256);
+    L.rec = align_up(L.groups + plan.groups_total * sizeof(u32), 256);
+    L.rec2 = align_up(L.rec + plan.rec_total * sizeof(u64), 256);
+    L.cta = align_up(L.rec2 + plan.rec_total * sizeof(u32), 256);
+    L.total = align_up(L.cta + plan.cta_total * sizeof(CtaRec), 256) + 256;
+    return L;
+}
+
+size_t sa_span_scratch_bytes(const SpanPlan &plan) { return (size_t)span_layout(plan).total; }
+
+int sa_span_is_literal(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, u32 n_terms, bool *out) {
+    *out = false;
+    for (u32 t = 0; t < n_terms; t++) {
+        if (lens[t] == 0) return SA_OK;
+        u64 first = 0;
+        SA_CUDA(cudaMemcpyAsync(&first, d_lists + offs[t], sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+        SA_CUDA(cudaStreamSynchronize(ix->stream));
+        if ((first & SA_HDR_MASK) != 0) return SA_OK;
+    }
+    *out = n_terms > 0;
+    return SA_OK;
+}
+
+int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, const SpanQuery *d_qs,
+                    SpanCounts *d_counts, void *d_scratch, float *dense_rows, u64 stride) {
+    const u32 Q = (u32)plan.qs.size();
+    if (Q == 0) return SA_OK;
+    SA_CHECK(plan.groups_total < 0xFFFFFFFFull && plan.words_total < 0xFFFFFFFFull, "slop query too large");
+    const SpanLayout L = span_layout(plan);
+    char *base = (char *)d_scratch;
     SpanArgs a;
+    memset(&a, 0, sizeof(a));
     a.words = d_lists;
-    a.queries = ix->queries.as<SpanQuery>();
-    a.counts = ix->cand_meta.as<SpanCounts>();
-    a.word_arena = ix->phrase_scratch.as<u64>();
-    a.group_arena = (u32 *)(a.word_arena + words_total);
-    a.out = ix->dense.as<float>();
+    a.tile_dir = (d_lists == ix->d_words) ? ix->d_tile_dir : nullptr;
+    a.queries = d_qs;
+    a.counts = d_counts;
+    a.word_arena = (u64 *)(base + L.words);
+    a.group_arena = (u32 *)(base + L.groups);
+    a.rec = (u64 *)(base + L.rec);
+    a.rec2 = (u32 *)(base + L.rec2);
+    a.cta = (CtaRec *)(base + L.cta);
+    a.out = dense_rows;
     a.out_stride = stride;
     a.n_docs = ix->n_docs;
     a.doc_base = ix->doc_base;
-    {
-        KernelTimer t(ix, 2);
-        // the reference's header-0 underflow corner (see span_candidates_literal_kernel)
-        bool literal = true;
-        for (u32 t = 0; t < n_terms; t++) {
-            u64 first = 0;
-            if (sq.len[t] == 0) { literal = false; break; }
-            SA_CUDA(cudaMemcpyAsync(&first, d_lists + sq.off[t], sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
-            SA_CUDA(cudaStreamSynchronize(ix->stream));
-            if ((first & SA_HDR_MASK) != 0) { literal = false; break; }
-        }
-        if (literal) {
-            const u64 cap3 = 3 * sq.len[0] + 3 * shortest_len + 16;
-            DevBuf lit;
-            if ((rc = lit.reserve((9 * cap3 + 8 * cap3) * sizeof(u64)))) return rc;
-            span_candidates_literal_kernel<<<1, 1, 0, ix->stream>>>(a, lit.as<u64>(), cap3);
-            SA_CUDA(cudaGetLastError());
-            SA_CUDA(cudaStreamSynchronize(ix->stream));
-            lit.release();
-        } else {
-            span_candidates_kernel<<<1, CAND_THREADS, 0, ix->stream>>>(a);
-            SA_CUDA(cudaGetLastError());
-        }
-        span_groups_build_kernel<<<1, CAND_THREADS, 0, ix->stream>>>(a);
+    SA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)Q * sizeof(SpanCounts), ix->stream));
+    SA_CUDA(cudaMemsetAsync(dense_rows, 0, (size_t)Q * stride * sizeof(float), ix->stream));
+    KernelTimer t(ix, 2);
+    if (plan.max_ctas) {
+        dim3 grid(plan.max_ctas, Q);
+        span_presence_kernel<<<grid, GEN_THREADS, 0, ix->stream>>>(a);
         SA_CUDA(cudaGetLastError());
-        SA_CUDA(cudaFuncSetAttribute(span_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(SPAN_WARPS * sizeof(WarpSpans))));
-        const u32 blocks = (u32)std::max<u64>(1, std::min<u64>((u64)ix->num_sms * 2, (5 * shortest_len + SPAN_WARPS - 1) / SPAN_WARPS));
-        span_groups_kernel<<<blocks, SPAN_WARPS * 32, SPAN_WARPS * sizeof(WarpSpans), ix->stream>>>(a, 1);
+        span_scan_kernel<<<Q, GEN_THREADS, 0, ix->stream>>>(a);
         SA_CUDA(cudaGetLastError());
-        t.stop();
+        span_write_kernel<<<grid, GEN_THREADS, 0, ix->stream>>>(a);
+        SA_CUDA(cudaGetLastError());
         ix->stats.phrase_kernel_launches += 3;
         ix->stats.total_launches += 3;
     }
+    if (plan.any_literal) {
+        // the reference's header-0 underflow corner (see span_candidates_literal_kernel)
+        for (u32 q = 0; q < Q; q++) {
+            const SpanQuery &sq = plan.qs[q];
+            if (!sq.literal) continue;
+            const u64 cap3 = 3 * sq.len[0] + 3 * sq.len[sq.shortest] + 16;
+            DevBuf lit;
+            int rc;
+            if ((rc = lit.reserve((9 * cap3 + 8 * cap3) * sizeof(u64)))) return rc;
+            span_candidates_literal_kernel<<<1, 1, 0, ix->stream>>>(a, q, lit.as<u64>(), cap3);
+            SA_CUDA(cudaGetLastError());
+            span_groups_build_kernel<<<1, GEN_THREADS, 0, ix->stream>>>(a, q);
+            SA_CUDA(cudaGetLastError());
+            SA_CUDA(cudaStreamSynchronize(ix->stream));
+            lit.release();
+            ix->stats.phrase_kernel_launches += 2;
+            ix->stats.total_launches += 2;
+        }
+    }
+    SA_CUDA(cudaFuncSetAttribute(span_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SPAN_WARPS * sizeof(WarpSpans))));
+    const u64 max_iters = std::max<u64>(1, 5 * plan.max_shortest);
+    const u64 want = (max_iters + SPAN_WARPS - 1) / SPAN_WARPS;
+    const u64 budget = std::max<u64>(8, (u64)ix->num_sms * 4 / Q);
+    dim3 grid2((unsigned)std::max<u64>(1, std::min<u64>(want, budget)), Q);
+    span_groups_kernel<<<grid2, SPAN_WARPS * 32, SPAN_WARPS * sizeof(WarpSpans), ix->stream>>>(a);
+    SA_CUDA(cudaGetLastError());
+    t.stop();
+    ix->stats.phrase_kernel_launches += 1;
+    ix->stats.total_launches += 1;
+    return SA_OK;
+}
+
+// Span search of one query into ix->dense row 0 (raw counts).  Caller holds ix->mu.
+int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, const u64 *dir_offs,
+                uint32_t n_terms, uint32_t slop, bool literal, u32 *n_undefined) {
+    const u64 stride = padded_stride(ix->n_docs);
+    int rc;
+    if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
+    SpanPlan plan;
+    sa_span_plan_add(plan, offs, lens, dir_offs, n_terms, slop, 0.0f, literal);
+    if ((rc = ix->phrase_scratch.reserve(sa_span_scratch_bytes(plan)))) return rc;
+    if ((rc = ix->queries.reserve(sizeof(SpanQuery)))) return rc;
+    if ((rc = ix->cand_meta.reserve(sizeof(SpanCounts)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->queries.p, plan.qs.data(), sizeof(SpanQuery), cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = sa_span_enqueue(ix, d_lists, plan, ix->queries.as<SpanQuery>(), ix->cand_meta.as<SpanCounts>(),
+                              ix->phrase_scratch.p, ix->dense.as<float>(), stride))) return rc;
     SpanCounts h;
     SA_CUDA(cudaMemcpyAsync(&h, ix->cand_meta.p, sizeof(h), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));

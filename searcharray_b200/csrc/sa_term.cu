@@ -242,8 +242,10 @@ term_tile_kernel(const TermBatchArgs a) {
 // Top-k candidate collection for an already materialised dense score vector (phrase queries:
 // their kernel scatters sparse matches, so the collector runs as a separate tile scan).  Same
 // outputs as step 3/4 of term_tile_kernel: per-tile candidate slots, count and maximum.
+template <bool SCORE>
 __global__ void __launch_bounds__(SA_TERM_THREADS)
-dense_topk_tiles_kernel(const float *__restrict__ dense, u64 stride, u32 row0, const TopkCtx t) {
+dense_topk_tiles_kernel(float *__restrict__ dense, u64 stride, u32 row0, const TopkCtx t,
+                        const float *__restrict__ norm, const float *__restrict__ row_idf) {
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
     const u32 q = blockIdx.y + row0;
@@ -252,13 +254,25 @@ dense_topk_tiles_kernel(const float *__restrict__ dense, u64 stride, u32 row0, c
     const u32 tile_doc0 = tile * SA_TILE_DOCS;
     const u32 k = t.k;
     constexpr int NV = SA_TILE_DOCS / SA_TERM_THREADS / 4;
-    const float4 *__restrict__ src = reinterpret_cast<const float4 *>(dense + (u64)q * stride + tile_doc0);
+    float4 *__restrict__ src = reinterpret_cast<float4 *>(dense + (u64)q * stride + tile_doc0);
     float4 v[NV];
     u32 my_max = 0;
+    const float idf = SCORE ? row_idf[blockIdx.y] : 0.0f;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
         v[j] = __ldcs(src + tid + j * SA_TERM_THREADS);
-        const float vs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        float vs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        if (SCORE) {
+            // raw counts -> BM25 (bm25.pyx:20-25; a zero count scores +0.0 for ordinary parameters)
+            if ((vs[0] != 0.0f) | (vs[1] != 0.0f) | (vs[2] != 0.0f) | (vs[3] != 0.0f)) {
+                const u32 d0 = tile_doc0 + (tid + j * SA_TERM_THREADS) * 4;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (vs[e] != 0.0f) vs[e] = bm25_from_norm(vs[e], __ldg(norm + d0 + e), idf);
+                v[j] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+                __stcs(src + tid + j * SA_TERM_THREADS, v[j]);
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; e++)
             if (vs[e] > 0.0f) my_max = max(my_max, __float_as_uint(vs[e]));
@@ -299,11 +313,13 @@ dense_topk_tiles_kernel(const float *__restrict__ dense, u64 stride, u32 row0, c
     }
 }
 
-int launch_dense_topk_tiles(sa_index *ix, const float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t) {
+int launch_dense_topk_tiles(sa_index *ix, float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t,
+                            const float *d_row_idf) {
     if (n_rows == 0 || t.n_tiles == 0) return SA_OK;
     dim3 grid(t.n_tiles, n_rows);
     KernelTimer tm(ix, 1);
-    dense_topk_tiles_kernel<<<grid, SA_TERM_THREADS, 0, ix->stream>>>(dense, stride, row0, t);
+    if (d_row_idf) dense_topk_tiles_kernel<true><<<grid, SA_TERM_THREADS, 0, ix->stream>>>(dense, stride, row0, t, ix->d_norm, d_row_idf);
+    else dense_topk_tiles_kernel<false><<<grid, SA_TERM_THREADS, 0, ix->stream>>>(dense, stride, row0, t, nullptr, nullptr);
     SA_CUDA(cudaGetLastError());
     tm.stop();
     ix->stats.topk_kernel_launches++;

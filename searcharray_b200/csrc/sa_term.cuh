@@ -43,7 +43,10 @@ int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len);
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys,
                        const u32 *d_out_index);
 u32 sa_topk_slots(u32 k);
-int launch_dense_topk_tiles(sa_index *ix, const float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t);
+// d_row_idf != NULL: the rows hold raw match counts; BM25 (norm table of the last sa_ensure_norm) is applied in
+// place on the way (row_idf[i] = idf of row row0 + i)
+int launch_dense_topk_tiles(sa_index *ix, float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t,
+                            const float *d_row_idf);
 int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
 // batch plumbing shared by sa_index.cu / sa_comm.cu (callers hold ix->mu)
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
