@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -93,16 +93,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def count_since(self, t_from):
+        return sum(1 for t, _ in self.lines if t >= t_from)
+
+    def stop(self, t_from=0.0):
+        """Summary of the samples taken at or after t_from (the start of the timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if t < t_from:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -218,8 +224,11 @@ def bench_ours(args, rank, world):
     if world > 1:
         # NCCL_DEBUG=VERSION (some images default to it) prints a banner on STDOUT, which would
         # break the one-JSON-line contract
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # ... and WARN still prints the version line.  Unset means silent; whatever level the user
+        # asked for goes to a file instead of stdout.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sa_b200_nccl_%h_%p.log")
         # Rendezvous for the NCCL unique id without any framework: all ranks of one launch share a
         # node (contract: --nnodes=1) and a parent (the torchrun agent), so rank 0 publishes the id
         # in a file keyed by MASTER_PORT + parent pid and the others poll for it.
@@ -288,7 +297,10 @@ def bench_ours(args, rank, world):
         execute()
         return download()
 
-    # ---- warm-up (>= 3 full steps)
+    # ---- warm-up (>= 3 full steps); the clock sampler (nvidia-smi -lms) starts here so that it is
+    #      already delivering samples when the timed region begins
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     overflow = 0
     for _ in range(max(args.warmup, 3)):
         overflow += e2e_step()
@@ -297,9 +309,8 @@ def bench_ours(args, rank, world):
     stats = _lib.SaStats()
     upload()
     _lib.check(L.sa_stats_reset(h))
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     barrier()
+    t_timed = time.time()
     _lib.check(L.sa_timer_start(h))
     for _ in range(args.steps):
         execute()
@@ -307,7 +318,6 @@ def bench_ours(args, rank, world):
     _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
     barrier()
     dev_ms = max_over_ranks(ms.value)
-    clk = clocks.stop()
     _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
     launches_value = int(stats.total_launches)
     download()
@@ -321,6 +331,19 @@ def bench_ours(args, rank, world):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = args.steps * Q / e2e_s
+    # clocks: samples taken during the two timed regions (device-timed steps + e2e steps).  When those
+    # are shorter than a few sampling periods (many GPUs, small shards) the same step is repeated,
+    # untimed, for ~0.4 s so that the clocks under this load are still observed.
+    clock_note = "sampled during the timed regions"
+    if clocks.count_since(t_timed) < 4:
+        n_extra = int(min(2000, max(1, 0.4 / max(dev_ms / 1e3 / args.steps, 1e-5))))
+        for _ in range(n_extra):
+            execute()
+        barrier()
+        download()
+        clock_note = f"timed regions too short to sample: + {n_extra} untimed repeats of the same step"
+    clk = clocks.stop(t_timed)
+    clk["note"] = clock_note
     h2d = int(term_ids.nbytes + starts.nbytes + idf.nbytes + Q * 24)     # + TermQuery descriptors
     d2h = int(Q * k * 8 + Q * 4)
 
