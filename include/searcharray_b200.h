@@ -171,6 +171,44 @@ int sa_score_batch_topk_allgather(sa_index *index, const uint32_t *terms, const 
                                   float avg_doc_len, float k1, float b, uint32_t k,
                                   uint32_t *out_docs, float *out_scores);
 
+/* ------------------------------------------------------ multi-field edismax (8f-1)
+ * Replaces the numpy half of searcharray/solr.py:117-355 (edismax): the per-(term, field) BM25
+ * vectors, the phrase-phase vectors and the combined score vector stay in HBM.  The host mirror
+ * (searcharray_b200/solr.py) parses the query like solr.py:77-114, computes idf like
+ * similarity.py:19-21 and drives these calls.  All fields index the same documents.
+ *   sa_multi_qf       solr.py:117-178.  field f has n_terms[f] query terms; term_ids / idf are the
+ *                     per-field lists concatenated.  has_boost[f] == 0 <=> "field" without ^boost.
+ *                     mm[f]: clauses that must score > 0 (term-centric: mm[0] over term positions;
+ *                     field-centric: per field, already clamped to its term count).  The combined
+ *                     vector is float64 (term-centric) or float32 (field-centric), as in numpy.
+ *   sa_multi_filter   solr.py:326-330: restrict field `field`'s posting lists of `term_ids` to the docs
+ *                     with qf > 0 (FilteredPosns, middle_out.py:291-317); df_out = doc frequencies of
+ *                     the filtered lists (what SearchArray.docfreq reports on the sliced array).
+ *   sa_multi_phrases  phrase i = filtered lists term_slots[phrase_starts[i] .. phrase_starts[i+1])
+ *                     (slots index the last sa_multi_filter's term list; term_ids: the same terms' ids);
+ *                     BM25 with idf[i].  Row i of the field holds the result (solr.py:181-244).
+ *   sa_multi_add_phase  float32 sum, in order, of rows (entry_field[i], entry_row[i]) * entry_boost[i],
+ *                     added to the combined vector where it is non-zero (solr.py:335-353).
+ *   sa_multi_download / sa_multi_topk   the dense vector (float64, or float32 when as_float32), or its
+ *                     exact top-k (score desc, doc asc; absolute doc ids; empty slots SA_NO_DOC / 0). */
+typedef struct sa_multi sa_multi;
+int sa_multi_create(sa_index *const *fields, uint32_t n_fields, sa_multi **multi_out);
+int sa_multi_destroy(sa_multi *multi);
+int sa_multi_qf(sa_multi *multi, int field_centric, const uint32_t *n_terms, const uint32_t *term_ids,
+                const float *idf, const float *boost, const uint32_t *has_boost,
+                const float *avg_doc_len, const float *k1, const float *b, const uint32_t *mm,
+                double tie, uint64_t *n_matches);
+int sa_multi_filter(sa_multi *multi, uint32_t field, const uint32_t *term_ids, uint32_t n_terms,
+                    uint64_t *df_out);
+int sa_multi_phrases(sa_multi *multi, uint32_t field, uint32_t n_phrases, const uint32_t *phrase_starts,
+                     const uint32_t *term_slots, const uint32_t *term_ids, const float *idf,
+                     float avg_doc_len, float k1, float b);
+int sa_multi_add_phase(sa_multi *multi, uint32_t n_entries, const uint32_t *entry_field,
+                       const uint32_t *entry_row, const float *entry_boost, const uint32_t *entry_has_boost);
+int sa_multi_download(sa_multi *multi, void *out, int as_float32);
+int sa_multi_is_float32(sa_multi *multi, int *out);
+int sa_multi_topk(sa_multi *multi, uint32_t k, uint32_t *out_docs, double *out_scores);
+
 /* ------------------------------------------------- per-op exports (parity tests)
  * Device implementations of the reference's native ops on raw arrays (host in, host out),
  * for kernel-level parity tests against the Cython originals. */

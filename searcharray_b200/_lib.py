@@ -64,6 +64,16 @@ SIGNATURES = {
     "sa_batch_download_allgather": (c_int, [P_void, P_u32, P_f32, P_u32]),
     "sa_score_batch_topk_allgather": (c_int, [P_void, P_u32, P_u32, P_f32, c_u32, c_u32, c_f32, c_f32, c_f32,
                                               c_u32, P_u32, P_f32]),
+    "sa_multi_create": (c_int, [ctypes.POINTER(P_void), c_u32, ctypes.POINTER(P_void)]),
+    "sa_multi_destroy": (c_int, [P_void]),
+    "sa_multi_qf": (c_int, [P_void, c_int, P_u32, P_u32, P_f32, P_f32, P_u32, P_f32, P_f32, P_f32, P_u32,
+                            ctypes.c_double, P_u64]),
+    "sa_multi_filter": (c_int, [P_void, c_u32, P_u32, c_u32, P_u64]),
+    "sa_multi_phrases": (c_int, [P_void, c_u32, c_u32, P_u32, P_u32, P_u32, P_f32, c_f32, c_f32, c_f32]),
+    "sa_multi_add_phase": (c_int, [P_void, c_u32, P_u32, P_u32, P_f32, P_u32]),
+    "sa_multi_download": (c_int, [P_void, P_void, c_int]),
+    "sa_multi_is_float32": (c_int, [P_void, ctypes.POINTER(c_int)]),
+    "sa_multi_topk": (c_int, [P_void, c_u32, P_u32, ctypes.POINTER(ctypes.c_double)]),
     "sa_op_popcount64_reduce": (c_int, [P_u64, c_u64, c_int, P_u64, P_f32, P_u64]),
     "sa_op_bm25_score": (c_int, [P_f32, P_f32, c_u64, c_f32, c_f32, c_f32, c_f32, c_int]),
     "sa_op_bigram_freqs": (c_int, [P_u64, c_u64, P_u64, c_u64, c_int, c_int, P_u64, P_f32, P_u64, P_u64, P_u64]),

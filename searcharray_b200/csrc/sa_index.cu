@@ -452,6 +452,9 @@ static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     return tq;
 }
 
+Bm25Params sa_make_bm25(const sa_index *ix, float idf, float avg_doc_len, float k1, float b) { return make_bm25(ix, idf, avg_doc_len, k1, b); }
+TermQuery sa_make_term_query(const sa_index *ix, u32 term_id, float idf) { return make_term_query(ix, term_id, idf); }
+
 static u32 n_tiles_of(const sa_index *ix) { return (u32)((ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS); }
 
 static size_t cand_bytes(const sa_index *ix, u32 Q, u32 slots) {

@@ -43,6 +43,8 @@ int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len);
 int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_base, u64 *d_out_keys,
                        const u32 *d_out_index);
 u32 sa_topk_slots(u32 k);
+Bm25Params sa_make_bm25(const sa_index *ix, float idf, float avg_doc_len, float k1, float b);
+TermQuery sa_make_term_query(const sa_index *ix, u32 term_id, float idf);
 // d_row_idf != NULL: the rows hold raw match counts; BM25 (norm table of the last sa_ensure_norm) is applied in
 // place on the way (row_idf[i] = idf of row row0 + i)
 int launch_dense_topk_tiles(sa_index *ix, float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t,
