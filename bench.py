@@ -486,6 +486,78 @@ def bench_ours(args, rank, world):
                                       "sample": f"{nsamp} slop-0 and {nslop} slop-2 queries of the step, one thread"}
         upload()          # restore the term batch for the sections below
 
+    # ---- edismax (the shape of BASELINE configs[4], on this run's corpus size): two fields, mixed
+    #      2-5 term queries, qf + pf + pf2 + pf3, mm=2, tie=0.3 (reference test_msmarco.py:436-443);
+    #      per query: sa_multi_* calls from the host mirror, top-k back (all-gathered over the shards)
+    edis = None
+    if args.edismax_queries > 0:
+        import pandas as pd
+        from searcharray_b200 import SearchArray, solr, synth
+        from searcharray_b200.shard import ShardComm
+        t0 = time.time()
+        tspec = synth.SynthSpec(args.docs, field="title")
+        thost, _, _ = synth.generate_shard(tspec, rank, world)
+        ttotal = 0.0
+        for blk in range(synth.N_BLOCKS):
+            ttotal += float(np.sum(synth.gen_doc_lens(args.docs, blk, "title"), dtype=np.float64))
+        t_avgdl = np.float32(ttotal / args.docs)
+        comm = ShardComm(h, rank, world)
+        body = SearchArray.from_host_index(host, device=local_rank, doc_base=lo, corpus_size=args.docs,
+                                           avg_doc_length=avgdl, global_df=df, comm=comm)
+        body._shared["dev"] = dev                      # the body shard is already in HBM
+        title = SearchArray.from_host_index(thost, device=local_rank, doc_base=lo, corpus_size=args.docs,
+                                            avg_doc_length=t_avgdl, comm=comm)
+        tdev = title._device()
+        tdf = np.zeros(thost.n_terms, dtype=np.uint64)
+        for t in range(thost.n_terms):
+            _lib.check(L.sa_docfreq(tdev.handle, t, ctypes.byref(tmp)))
+            tdf[t] = tmp.value
+        title.global_df = comm.sum_u64(tdf)
+        frame = pd.DataFrame({"title": title, "body": body})
+        log(f"edismax: title field {thost.words.nbytes / 1e6:.0f} MB of postings, avgdl={t_avgdl}, "
+            f"set-up {time.time() - t0:.1f}s")
+        eq = synth.edismax_queries(spec, args.edismax_queries)
+        ekw = dict(qf=["title^1.0", "body^0.5"], pf=["body"], pf2=["body"], pf3=["body"], mm=2, tie=0.3)
+        for qtext in eq[:3]:
+            solr.edismax_topk(frame, qtext, k=k, **ekw)
+        barrier()
+        t0 = time.perf_counter()
+        hits = 0
+        for qtext in eq:
+            d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
+            hits += int(d_[0] != 0xFFFFFFFF)
+        barrier()
+        e_s = max_over_ranks(time.perf_counter() - t0)
+        edis = {"workload": "two-field edismax (title^1.0 body^0.5, pf/pf2/pf3 on body, mm=2, tie=0.3), mixed 2-5 term "
+                            "queries, exact float64 top-%d, per-query host-driven sa_multi_* calls" % k,
+                "queries": len(eq), "e2e": {"value": len(eq) / e_s, "unit": "queries/s"},
+                "ms_per_query": 1e3 * e_s / len(eq), "queries_with_hits": hits}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import search as osearch, solr as osolr
+            ofields = {}
+            for name, hidx, adl in (("title", thost, t_avgdl), ("body", host, avgdl)):
+                oi = osearch.OracleIndex({t: hidx.term_words(t) for t in range(hidx.n_terms)}, hidx.doc_lens,
+                                         avg_doc_length=adl, corpus_size=args.docs, cache=True)
+                ofields[name] = osolr.OracleField(oi, hidx.term_dict.term_to_ids)
+            nq = min(2, len(eq))
+            t0 = time.perf_counter()
+            bad = 0
+            for qtext in eq[:nq]:
+                want = osolr.edismax(ofields, qtext, **ekw)
+                d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
+                order = np.lexsort((np.arange(len(want)), -want))[:k]
+                order = order[want[order] > 0]
+                if not (np.array_equal(d_[:len(order)], order.astype(np.uint32)) and
+                        np.allclose(s_[:len(order)], want[order], rtol=1e-5, atol=0)):
+                    bad += 1
+            dt = time.perf_counter() - t0
+            edis["cpu_baseline"] = {"kind": "port", "cores": 1, "value": nq / dt, "unit": "queries/s",
+                                    "sample": f"{nq} of the queries, oracle port of solr.py (includes the GPU "
+                                              "re-run used for the parity check, negligible)",
+                                    "gpu_topk_mismatches": bad}
+        upload()          # restore the term batch for the sections below
+        del frame, title, tdev
+
     # ---- e2e_dense: the literal .score() drop-in, dense float32[N] to the host per query
     e2e_dense = None
     if rank == 0 and world == 1:
@@ -564,6 +636,7 @@ def bench_ours(args, rank, world):
             "cpu_baseline": cpu,
             "e2e_dense": e2e_dense,
             "phrase": phrase,
+            "edismax": edis,
             "topk_overflow_reruns": int(overflow),
             "verify": verify,
         }
@@ -584,6 +657,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phrase-queries", type=int, default=256)
     ap.add_argument("--slop-queries", type=int, default=16)
+    ap.add_argument("--edismax-queries", type=int, default=48)
     ap.add_argument("--verify", type=int, default=0,
                     help="rank 0 re-generates the FULL corpus and checks this many queries' global top-k "
                          "against the CPU oracle (parity of the sharded / all-gathered path)")

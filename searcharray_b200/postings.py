@@ -183,6 +183,11 @@ class SearchArray(ExtensionArray):
         self.corpus_size = host.n_docs
         self.rows = None                 # sliced view: local doc ids (postings.py:344-358)
         self._bm25_doc_lens = None
+        # doc-range shard of a larger corpus: absolute id of row 0, and the GLOBAL
+        # statistics idf / BM25 must use (set by from_host_index; None = this array is the corpus)
+        self.doc_base = 0
+        self.global_df = None            # uint64[n_terms] document frequencies over all shards
+        self.comm = None                 # shard.ShardComm: sums over ranks where a query needs them
         self._shared = {"dev": None, "lock": threading.Lock()}   # shared by views/copies
 
     @classmethod
@@ -198,12 +203,23 @@ class SearchArray(ExtensionArray):
         return cls.from_host_index(host, tokenizer=tokenizer, avoid_copies=avoid_copies, device=device)
 
     @classmethod
-    def from_host_index(cls, host: HostIndex, tokenizer=ws_tokenizer, avoid_copies=True, device=0):
+    def from_host_index(cls, host: HostIndex, tokenizer=ws_tokenizer, avoid_copies=True, device=0,
+                        doc_base=0, corpus_size=None, avg_doc_length=None, global_df=None, comm=None):
+        """Wraps a prebuilt HostIndex.  For one doc-range shard of a larger corpus pass the shard's
+        first absolute doc id and the global corpus size / average doc length / per-term document
+        frequencies (idf must not depend on the sharding)."""
         obj = cls.__new__(cls)
         obj.tokenizer = tokenizer
         obj.avoid_copies = avoid_copies
         obj.device = device
         obj._set_host(host)
+        obj.doc_base = int(doc_base)
+        if corpus_size is not None:
+            obj.corpus_size = int(corpus_size)
+        if avg_doc_length is not None:
+            obj.avg_doc_length = avg_doc_length
+        obj.global_df = None if global_df is None else np.asarray(global_df, dtype=np.uint64)
+        obj.comm = comm
         return obj
 
     def _device(self) -> DeviceIndex:
@@ -211,7 +227,7 @@ class SearchArray(ExtensionArray):
         if sh["dev"] is None:
             with sh["lock"]:
                 if sh["dev"] is None:
-                    sh["dev"] = DeviceIndex(self.host, device=self.device)
+                    sh["dev"] = DeviceIndex(self.host, device=self.device, doc_base=self.doc_base)
         return sh["dev"]
 
     def __getstate__(self):
@@ -365,6 +381,8 @@ class SearchArray(ExtensionArray):
         tid = self._term_id(token)
         if tid == _lib.NO_TERM:
             return 0
+        if self.global_df is not None and self.rows is None:
+            return np.uint64(self.global_df[tid])
         dev = self._device()
         df = ctypes.c_uint64(0)
         with self._shared["lock"]:

@@ -34,3 +34,40 @@ def unpack_keys(keys):
     scores = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32)
     docs = np.where(keys == 0, np.uint32(0xFFFFFFFF), docs)
     return docs, scores
+
+
+class ShardComm:
+    """The few host-visible reductions a sharded query needs, over the NCCL communicator attached
+    to one sa_index handle (sa_comm_init).  Everything exchanged is O(terms) or O(k) per query; the
+    score vectors never leave their GPU."""
+
+    def __init__(self, handle, rank, world):
+        self.handle, self.rank, self.world = handle, rank, world
+
+    def sum_u64(self, values):
+        from . import _lib
+        a = np.ascontiguousarray(values, dtype=np.uint64).copy()
+        if self.world > 1 and a.size:
+            _lib.check(_lib.lib().sa_comm_allreduce_sum_u64(self.handle, _lib.p_u64(a), a.size))
+        return a
+
+    def allgather_u64(self, values):
+        """[n] per rank -> [world, n] on every rank (a sum over disjoint slots)."""
+        v = np.ascontiguousarray(values, dtype=np.uint64)
+        buf = np.zeros((self.world, v.size), dtype=np.uint64)
+        buf[self.rank] = v
+        return self.sum_u64(buf.reshape(-1)).reshape(self.world, v.size)
+
+    def merge_topk_f64(self, docs, scores, k):
+        """Per-shard (absolute doc ids, float64 scores) -> the global k best on every rank
+        (score desc, doc asc), the single all-gather of per-shard top-k of SURVEY 8e."""
+        d = self.allgather_u64(np.asarray(docs, dtype=np.uint64)).reshape(-1)
+        s = self.allgather_u64(np.asarray(scores, dtype=np.float64).view(np.uint64)).reshape(-1).view(np.float64)
+        keep = d != 0xFFFFFFFF
+        d, s = d[keep], s[keep]
+        order = np.lexsort((d, -s))[:k]
+        out_d = np.full(k, 0xFFFFFFFF, dtype=np.uint32)
+        out_s = np.zeros(k, dtype=np.float64)
+        out_d[:len(order)] = d[order]
+        out_s[:len(order)] = s[order]
+        return out_d, out_s

@@ -224,7 +224,9 @@ def _run_device(plan: _Plan) -> _Multi:
                              _lib.p_f32(a_k1), _lib.p_f32(a_b), _lib.p_u32(a_mm), float(plan.tie),
                              ctypes.byref(n_matches)))
     phases = plan.phases()
-    if n_matches.value == 0 or not any(items for _, items in phases):
+    comm = plan.arrays[0].comm            # doc-range shards: match counts and filtered dfs are global
+    total_matches = n_matches.value if comm is None else int(comm.sum_u64([n_matches.value])[0])
+    if total_matches == 0 or not any(items for _, items in phases):
         return multi
 
     # every phrase of one field runs in one launch on that field's lists filtered to qf > 0
@@ -245,6 +247,8 @@ def _run_device(plan: _Plan) -> _Multi:
         u_ids = _u32([arr._term_id(t) for t in uniq])
         dfs = np.zeros(len(uniq), dtype=np.uint64)
         _lib.check(L.sa_multi_filter(multi.handle, fi, _lib.p_u32(u_ids), len(uniq), _lib.p_u64(dfs)))
+        if comm is not None:
+            dfs = comm.sum_u64(dfs)
         starts, slots, ids, p_idf = [0], [], [], []
         phrase_lists = {name: phrases for name, items in phases for ff, _, phrases, _ in items if ff == f}
         for r, (name, i) in enumerate(rows):
@@ -359,4 +363,7 @@ def edismax_topk(frame: pd.DataFrame, q: str, qf: List[str], k: int = 10, mm: Op
         multi = _run_device(plan)
         _lib.check(_lib.lib().sa_multi_topk(multi.handle, k, _lib.p_u32(docs),
                                             scores.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+    comm = plan.arrays[0].comm
+    if comm is not None:                  # one all-gather of the per-shard top-k, merged on every rank
+        return comm.merge_topk_f64(docs, scores, k)
     return docs, scores

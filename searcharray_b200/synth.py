@@ -32,10 +32,21 @@ def block_bounds(n_docs):
     return [(n_docs * b) // N_BLOCKS for b in range(N_BLOCKS + 1)]
 
 
-def gen_doc_lens(n_docs, block):
+# Fields of the two-field (edismax) corpus: the body is the MSMARCO-passage-like field above; the
+# title is a short field (mean ~ 6 tokens) over the SAME vocabulary with rarer terms (SURVEY 8d,
+# config 5).  `key` separates the fields' random streams; the body keeps key () so that the
+# single-field corpus is unchanged.
+FIELDS = {
+    "body": {"key": (), "len": (3.9, 0.45, 8, 400), "df_scale": 1.0, "plant_scale": 1.0},
+    "title": {"key": (101,), "len": (1.7, 0.4, 1, 30), "df_scale": 0.15, "plant_scale": 0.25},
+}
+
+
+def gen_doc_lens(n_docs, block, field="body"):
     lo, hi = block_bounds(n_docs)[block], block_bounds(n_docs)[block + 1]
-    r = _rng(0, block)
-    return np.clip(r.lognormal(3.9, 0.45, hi - lo), 8, 400).astype(np.float32)
+    mu, sigma, lo_len, hi_len = FIELDS[field]["len"]
+    r = _rng(*FIELDS[field]["key"], 0, block)
+    return np.clip(r.lognormal(mu, sigma, hi - lo), lo_len, hi_len).astype(np.float32)
 
 
 def _postings_for(rng, doc_lens, doc0, p, planted=None):
@@ -56,8 +67,9 @@ def _postings_for(rng, doc_lens, doc0, p, planted=None):
 class SynthSpec:
     """Names + generation parameters of every term of the synthetic vocabulary."""
 
-    def __init__(self, n_docs, terms_per_bucket=8, n_phrase_groups=8):
+    def __init__(self, n_docs, terms_per_bucket=8, n_phrase_groups=8, field="body"):
         self.n_docs = n_docs
+        self.field = field
         self.terms = []            # (name, df_fraction, phrase_group or -1, slot in group)
         for bi, p in enumerate(DF_BUCKETS):
             for j in range(terms_per_bucket):
@@ -89,7 +101,9 @@ def generate_shard(spec: SynthSpec, rank=0, world=1, progress=None):
     blocks = range(rank * per, (rank + 1) * per)
     bounds = block_bounds(spec.n_docs)
     doc_lo, doc_hi = bounds[blocks[0]], bounds[blocks[-1] + 1]
-    dl_blocks = {b: gen_doc_lens(spec.n_docs, b) for b in blocks}
+    fld = FIELDS[spec.field]
+    fkey = fld["key"]
+    dl_blocks = {b: gen_doc_lens(spec.n_docs, b, spec.field) for b in blocks}
     doc_lens = np.concatenate([dl_blocks[b] for b in blocks])
 
     # planted phrase occurrences per (group, block): docs that hold the rare term get the
@@ -98,8 +112,11 @@ def generate_shard(spec: SynthSpec, rank=0, world=1, progress=None):
     for g, ph in enumerate(spec.phrases):
         for b in blocks:
             dl = dl_blocks[b]
-            r = _rng(2, g, b)
-            docs = np.flatnonzero(r.random(len(dl), dtype=np.float32) < ph["rare_p"] * ph["plant_frac"])
+            r = _rng(*fkey, 2, g, b)
+            docs = np.flatnonzero(r.random(len(dl), dtype=np.float32) <
+                                  ph["rare_p"] * ph["plant_frac"] * fld["plant_scale"])
+            if spec.field != "body":
+                docs = docs[dl[docs] >= 4]                 # the phrase must fit
             start = (r.random(len(docs)) * np.maximum(dl[docs] - 4, 1)).astype(np.int64)
             plants[(g, b)] = (docs + bounds[b], start)
 
@@ -112,7 +129,7 @@ def generate_shard(spec: SynthSpec, rank=0, world=1, progress=None):
             if g >= 0:
                 pdocs, pstart = plants[(g, b)]
                 planted = (pdocs << 18) | (pstart + slot)
-            d, pos = _postings_for(_rng(1, ti, b), dl_blocks[b], bounds[b], p, planted)
+            d, pos = _postings_for(_rng(*fkey, 1, ti, b), dl_blocks[b], bounds[b], p * fld["df_scale"], planted)
             parts.append(encode_postings(d, pos))
         w = np.concatenate(parts) if len(parts) > 1 else parts[0]
         td.add_term(name)
@@ -145,3 +162,20 @@ def stratified_term_queries(spec: SynthSpec, n_queries, seed=11):
 def phrase_queries(spec: SynthSpec, n_queries, seed=12):
     r = _rng(4, seed)
     return [list(spec.phrases[int(r.integers(0, len(spec.phrases)))]["terms"]) for _ in range(n_queries)]
+
+
+def edismax_queries(spec: SynthSpec, n_queries, seed=13):
+    """Mixed 2-5 term queries for the two-field edismax workload: a run of
+    2-4 terms of a planted phrase group (so pf / pf2 / pf3 find matches), optionally followed by a
+    term of the single-term vocabulary."""
+    r = _rng(5, seed)
+    out = []
+    for _ in range(n_queries):
+        ph = spec.phrases[int(r.integers(0, len(spec.phrases)))]["terms"]
+        n = int(r.integers(2, 5))
+        at = int(r.integers(0, 4 - n + 1))
+        toks = list(ph[at:at + n])
+        if r.random() < 0.5:
+            toks.append(spec.query_terms[int(r.integers(0, len(spec.query_terms)))])
+        out.append(" ".join(toks))
+    return out
