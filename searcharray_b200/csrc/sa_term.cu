@@ -80,6 +80,24 @@ term_tile_kernel(const TermBatchArgs a) {
         hi = s_range[1];
     }
 
+    // Dense tiles (SCORE mode): instead of one dependent norm gather per matching doc, the tile's
+    // norms are staged in the score tile itself with asynchronous 16-byte copies (cp.async) issued
+    // together with the first posting loads -- one coalesced 32 KB read in place of a second DRAM
+    // round trip per pass.  A doc's head reads its norm from the tile and stores the score NEGATED:
+    // norms are > 0 here and scores >= +0, so the sign bit tells a score (set) from a leftover norm
+    // (clear), which the flush turns into 0.
+    const bool staged_norm = MODE == TERM_MODE_SCORE && !ALL_DOCS && (hi - lo) >= a.staged_norm_min_words;
+    bool norm_ready = !staged_norm;
+    if (staged_norm) {
+        const float4 *__restrict__ n4 = reinterpret_cast<const float4 *>(a.norm + tile_doc0);
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<float4 *>(s_out) + tid + i * SA_TERM_THREADS);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(n4 + tid + i * SA_TERM_THREADS) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
     // 2. stream the slice.  Each warp takes windows of 30 owned words and loads 32 (two look-ahead
     //    lanes), so "is the previous / next word the same doc?" is a register shuffle with no
     //    warp-edge special case.  Words are sorted by doc: the thread holding the FIRST word of a
@@ -133,8 +151,13 @@ term_tile_kernel(const TermBatchArgs a) {
                     }
                 }
                 pk[u] = (rel << 18) | tf;
-                if (MODE == TERM_MODE_SCORE && !ALL_DOCS && tf) nr[u] = __ldg(norm + rel);
+                if (MODE == TERM_MODE_SCORE && !ALL_DOCS && tf && !staged_norm) nr[u] = __ldg(norm + rel);
             }
+        }
+        if (!norm_ready) {                                 // CTA-uniform: first pass of a staged tile
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            norm_ready = true;
         }
 #pragma unroll
         for (int u = 0; u < UN; u++) {
@@ -146,11 +169,12 @@ term_tile_kernel(const TermBatchArgs a) {
                 } else {
                     v = 0.0f;
                     if (tf) {
-                        v = bm25_from_norm((float)tf, nr[u], tq.idf);
+                        const float nrm = staged_norm ? s_out[rel] : nr[u];
+                        v = bm25_from_norm((float)tf, nrm, tq.idf);
                         my_max = max(my_max, __float_as_uint(v));
                     }
                 }
-                s_out[rel] = v;
+                s_out[rel] = staged_norm ? -v : v;
             }
         }
     };
@@ -197,6 +221,12 @@ term_tile_kernel(const TermBatchArgs a) {
     for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
         const unsigned g = tid + jj * SA_TERM_THREADS;
         float4 v = reinterpret_cast<const float4 *>(s_out)[g];
+        if (staged_norm) {                                  // sign set: a (negated) score; clear: a leftover norm
+            v.x = __float_as_int(v.x) < 0 ? -v.x : 0.0f;
+            v.y = __float_as_int(v.y) < 0 ? -v.y : 0.0f;
+            v.z = __float_as_int(v.z) < 0 ? -v.z : 0.0f;
+            v.w = __float_as_int(v.w) < 0 ? -v.w : 0.0f;
+        }
         if (ALL_DOCS && MODE == TERM_MODE_SCORE) {
             // bm25.pyx:20-25 over EVERY doc (NaN / inf / -0.0 cases of exotic parameters)
             Bm25Params p = a.bm25;
@@ -359,6 +389,10 @@ int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len) {
 int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
     if (n_queries == 0 || a_in.n_docs == 0) return SA_OK;
     TermBatchArgs a = a_in;
+    {
+        static const long env_thresh = getenv("SA_STAGED_NORM_MIN_WORDS") ? atol(getenv("SA_STAGED_NORM_MIN_WORDS")) : -1;
+        a.staged_norm_min_words = env_thresh >= 0 ? (u32)env_thresh : SA_STAGED_NORM_MIN_WORDS;
+    }
     a.tile_dir = ix->d_tile_dir;
     a.norm = ix->d_norm;
     const bool sparse_score = (a.mode == TERM_MODE_SCORE) && a.bm25.sparse_ok;

@@ -5,6 +5,7 @@
 #define SA_TILE_DOCS 8192          // docs per CTA tile (32 KB of float32 scores)
 #define SA_TERM_UNROLL 4           // 30-word windows loaded per warp before processing
 #define SA_TERM_THREADS 256
+#define SA_STAGED_NORM_MIN_WORDS 1024   // tiles with at least this many posting words stage the tile's norms (sa_term.cu)
 #define SA_TOPK_MAX 32             // warp-level threshold estimation handles k <= 32
 
 enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
@@ -35,6 +36,7 @@ struct TermBatchArgs {
     u64 min_payload, max_payload;
     int filter;                 // apply the payload_slice filter
     int mode;
+    u32 staged_norm_min_words;  // set by launch_term_batch
     TopkCtx topk;
 };
 

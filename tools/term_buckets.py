@@ -16,7 +16,7 @@ dev = DeviceIndex(host, 0, 0)
 h = dev.handle
 print('upload', time.time()-t0, flush=True)
 avgdl = float(np.mean(host.doc_lens))
-Q, k = 128, 10
+Q, k = (int(sys.argv[3]) if len(sys.argv) > 3 else 128), 10
 only = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else None
 for b, p in enumerate(synth.DF_BUCKETS):
     if only is not None and b not in only:
