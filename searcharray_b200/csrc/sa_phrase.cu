@@ -318,7 +318,6 @@ phrase_kernel(const PhraseArgs a) {
     __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
     __shared__ u32 s_top[(PT / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
-    __shared__ u64 s_m[2];
 
     const u32 q = blockIdx.y;
     const PhraseQuery &pq = a.queries[q];
@@ -460,22 +459,44 @@ phrase_kernel(const PhraseArgs a) {
     const u32 row = a.topk_row0 + q;
     const u32 tile0 = (u32)(((u64)blockIdx.x * a.docs_per_chunk) / SA_TILE_DOCS);
     const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
+    // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
+    // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
+    u64 cur = 0;
+    u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
     for (u32 tile = tile0; tile < tile1; tile++) {
-        const u64 t_abs0 = a.doc_base + (u64)tile * SA_TILE_DOCS, t_abs1 = t_abs0 + SA_TILE_DOCS;
-        if (tid < 2) {               // entries of fin.docs (sorted by doc) inside this tile
-            const u64 key = tid ? t_abs1 : t_abs0;
-            u64 lo = 0, hi = fin.n_docs;
-            while (lo < hi) {
-                u64 mid = (lo + hi) >> 1;
-                if ((fin.docs[mid] >> 32) < key) lo = mid + 1; else hi = mid;
+        const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
+        if (next_doc >= t_abs1) {
+            float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+            if (a.topk.k && tid == 0) {
+                const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                a.topk.tile_cnt[t_idx] = 0;
+                a.topk.tile_max[t_idx] = 0;
             }
-            s_m[tid] = lo;
+            continue;
         }
+        // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
+        const u64 m0 = cur;
+        u64 lo = cur + 1, hi = fin.n_docs, st = 1;
+        while (lo < hi) {
+            const u64 probe = min(lo + st - 1, hi - 1);
+            if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
+            else { hi = probe; break; }
+        }
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+        }
+        const u64 m1 = lo;
+        cur = m1;
+        next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
 #pragma unroll
         for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
             reinterpret_cast<float4 *>(s_tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        const u64 m0 = s_m[0], m1 = s_m[1];
         u32 my_max = 0;
         for (u64 i = m0 + tid; i < m1; i += PT) {
             const u64 e = fin.docs[i];
