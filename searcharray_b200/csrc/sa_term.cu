@@ -383,29 +383,6 @@ int sa_ensure_norm(sa_index *ix, float k1, float b, float avg_doc_len) {
     }
     ix->norm_k1 = k1; ix->norm_b = b; ix->norm_avgdl = avg_doc_len;
     ix->norm_valid = true;
-    // The norm table is the one randomly gathered structure of the scan (one 32-byte sector per
-    // matching doc) while every query streams 4*N bytes of scores through L2: pin the table in the
-    // persisting part of L2 (access policy window on the library stream) so the gathers stop going
-    // to DRAM.  Best effort: silently skipped where the device refuses.
-    static const bool persist = !(getenv("SA_L2_PERSIST_NORM") && atoi(getenv("SA_L2_PERSIST_NORM")) == 0);
-    if (persist && n_pad) {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, ix->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 &&
-            prop.accessPolicyMaxWindowSize > 0) {
-            const size_t bytes = n_pad * sizeof(float);
-            const size_t setaside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside);
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = ix->d_norm;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)setaside / (double)attr.accessPolicyWindow.num_bytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-            cudaGetLastError();
-        }
-    }
     return SA_OK;
 }
 
