@@ -658,13 +658,12 @@ int sa_batch_execute_locked(sa_index *ix) {
         if (B.slop > 0) {
             const SpanPlan &plan = B.span_plans[chunk_i++];
             if (C.n_phrase) {
-                // span counts into zeroed rows, then one tile pass scores them in place and collects top-k
+                // span matches become records; one tile pass writes the rows (zeros + BM25) and collects top-k
                 float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;
                 if ((rc = sa_ensure_norm(ix, B.k1, B.b, B.avg_doc_len))) return rc;
                 if ((rc = sa_span_enqueue(ix, ix->d_words, plan, B.d_sq.as<SpanQuery>() + C.phrase0,
-                                          B.d_scounts.as<SpanCounts>() + C.phrase0, ix->phrase_scratch.p, rows, stride))) return rc;
-                if ((rc = launch_dense_topk_tiles(ix, ix->dense.as<float>(), stride, C.n_term, C.n_phrase, t,
-                                                  B.d_sidf.as<float>() + C.phrase0))) return rc;
+                                          B.d_scounts.as<SpanCounts>() + C.phrase0, ix->phrase_scratch.p, rows, stride,
+                                          &t, C.n_term))) return rc;
             }
         } else if (C.n_phrase) {
             float *rows = ix->dense.as<float>() + (u64)C.n_term * stride;

@@ -52,9 +52,17 @@ struct SpanArgs {
     u64 *rec;                            // p | mask7 << 32 | put5 << 39 | start5 << 44
     u32 *rec2;                           // local word offset | local start rank << 16
     CtaRec *cta;
-    float *out;                          // [Q][out_stride] pre-zeroed: out[last_key - doc_base] += count
+    float *out;                          // [Q][out_stride]
     u64 out_stride;
     u64 n_docs, doc_base;
+    // matches != NULL: phase 2 writes one record (local doc << 32 | count) per iteration instead of
+    // adding into `out`; span_tiles_kernel then materialises the rows (BM25 + top-k collection)
+    u64 *matches;
+    const float *norm;
+    TopkCtx topk;
+    u32 topk_row0;
+    u32 n_chunks;                        // doc-range chunks per query of span_tiles_kernel
+    u64 docs_per_chunk;                  // a multiple of SA_TILE_DOCS
 };
 
 // first index in [0, len) whose header is >= target
@@ -656,11 +664,135 @@ span_groups_kernel(const SpanArgs a) {
             else add = collect_spans(S, cursor, n, max_w);
             if (lane == 0) {
                 const u64 d = (u64)last_key - a.doc_base;
-                if (d < a.n_docs) atomicAdd(a.out + (u64)q * a.out_stride + d, (float)add);
+                if (a.matches) a.matches[sq.m_off + it] = d < a.n_docs ? ((d << 32) | add) : ~0ull;
+                else if (d < a.n_docs) atomicAdd(a.out + (u64)q * a.out_stride + d, (float)add);
                 if (undefined) atomicAdd(&a.counts[q].undefined, 1u);
             }
             __syncwarp();
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------- phase 3 (batched path)
+// are the match records of every query in doc order?  (they are whenever the terms' doc groups pair up)
+__global__ void __launch_bounds__(GEN_THREADS)
+span_sorted_kernel(const SpanArgs a) {
+    const u32 q = blockIdx.y;
+    const SpanQuery &sq = a.queries[q];
+    const u32 iters = a.counts[q].n_groups[0];
+    const u64 *__restrict__ m = a.matches + sq.m_off;
+    bool bad = false;
+    for (u32 i = blockIdx.x * GEN_THREADS + threadIdx.x + 1; i < iters; i += gridDim.x * GEN_THREADS)
+        if ((m[i] >> 32) < (m[i - 1] >> 32) || m[i] == ~0ull || m[i - 1] == ~0ull) bad = true;
+    if (iters && threadIdx.x == 0 && blockIdx.x == 0 && m[0] == ~0ull) bad = true;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) a.counts[q].unsorted = 1;
+}
+
+// One CTA per (doc-range chunk, query): writes the chunk's dense tiles -- zeros, plus the BM25 of the
+// accumulated span counts where there are matches -- and collects every tile's top-k candidates.
+__global__ void __launch_bounds__(SA_TERM_THREADS)
+span_tiles_kernel(const SpanArgs a) {
+    __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
+    __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
+    __shared__ u32 s_ncand, s_tile_max;
+    const u32 q = blockIdx.y;
+    const SpanQuery &sq = a.queries[q];
+    const unsigned tid = threadIdx.x;
+    const u32 iters = a.counts[q].n_groups[0];
+    const bool sorted = a.counts[q].unsorted == 0;
+    const u64 *__restrict__ m = a.matches + sq.m_off;
+    const u32 row = a.topk_row0 + q;
+    float *out = a.out + (u64)row * a.out_stride;
+    const u32 n_tiles = (u32)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    const u32 tile0 = (u32)(((u64)blockIdx.x * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = min(n_tiles, (u32)((((u64)blockIdx.x + 1) * a.docs_per_chunk) / SA_TILE_DOCS));
+    // sorted records: cursor at the first record of this chunk (uniform bisect)
+    u64 cur = 0;
+    if (sorted) {
+        const u64 key = (u64)tile0 * SA_TILE_DOCS;
+        u64 lo = 0, hi = iters;
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((m[mid] >> 32) < key) lo = mid + 1; else hi = mid;
+        }
+        cur = lo;
+    }
+    u64 next_doc = (sorted && cur < iters) ? (m[cur] >> 32) : ~0ull;
+    for (u32 tile = tile0; tile < tile1; tile++) {
+        const u64 t0 = (u64)tile * SA_TILE_DOCS, t1 = t0 + SA_TILE_DOCS;
+        if (sorted && next_doc >= t1) {                                   // no match in this tile
+            float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + t0);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++) __stcs(out4 + tid + i * SA_TERM_THREADS, z);
+            if (a.topk.k && tid == 0) {
+                const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                a.topk.tile_cnt[t_idx] = 0;
+                a.topk.tile_max[t_idx] = 0;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
+            reinterpret_cast<float4 *>(s_tile)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        u32 n_items = 0;
+        if (sorted) {
+            u64 end = cur;                                                 // records of this tile: [cur, end)
+            {
+                u64 lo = cur + 1, hi = iters, st = 1;
+                while (lo < hi) {
+                    const u64 probe = min(lo + st - 1, hi - 1);
+                    if ((m[probe] >> 32) < t1) { lo = probe + 1; st <<= 1; }
+                    else { hi = probe; break; }
+                }
+                while (lo < hi) {
+                    const u64 mid = (lo + hi) >> 1;
+                    if ((m[mid] >> 32) < t1) lo = mid + 1; else hi = mid;
+                }
+                end = lo;
+            }
+            for (u64 i = cur + tid; i < end; i += SA_TERM_THREADS) {
+                const u64 e = m[i];
+                const u32 c = (u32)e;
+                if (c) atomicAdd(&s_tile[(e >> 32) - t0], (float)c);       // equal docs may repeat: counts add up
+            }
+            n_items = (u32)(end - cur);
+            cur = end;
+            next_doc = cur < iters ? (m[cur] >> 32) : ~0ull;
+        } else {
+            for (u32 i = tid; i < iters; i += SA_TERM_THREADS) {
+                const u64 e = m[i];
+                if (e == ~0ull) continue;
+                const u64 d = e >> 32;
+                if (d >= t0 && d < t1 && (u32)e) atomicAdd(&s_tile[d - t0], (float)(u32)e);
+            }
+            n_items = SA_TILE_DOCS;                                        // unknown: always derive a bound
+        }
+        __syncthreads();
+        // counts -> BM25 in place (bm25.pyx:20-25 with the precomputed length norm); each thread owns
+        // the elements it will flush
+        u32 my_max = 0;
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++) {
+            const unsigned g = tid + i * SA_TERM_THREADS;
+            float4 v = reinterpret_cast<float4 *>(s_tile)[g];
+            if ((v.x != 0.0f) | (v.y != 0.0f) | (v.z != 0.0f) | (v.w != 0.0f)) {
+                float vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (vs[e] != 0.0f) {
+                        const float nrm = __ldg(a.norm + t0 + g * 4 + e);
+                        vs[e] = __fmul_rn(__fdiv_rn(vs[e], __fadd_rn(vs[e], nrm)), sq.idf);
+                        if (vs[e] > 0.0f) my_max = max(my_max, __float_as_uint(vs[e]));
+                    }
+                }
+                reinterpret_cast<float4 *>(s_tile)[g] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+            }
+        }
+        __syncthreads();
+        flush_tile_collect(s_tile, out + t0, a.topk, row, tile, my_max, n_items, s_top, &s_ncand, &s_tile_max);
     }
 }
 
@@ -691,6 +823,8 @@ void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u6
         plan.words_total += sq.s_cap[t] + 2;
         plan.groups_total += sq.s_cap[t] + 2;
     }
+    sq.m_off = plan.match_total;
+    plan.match_total += (n_terms ? sq.s_cap[0] : 0) + 2;                 // one record per doc group of term 0
     sq.n_ctas = literal ? 0u : (u32)((shortest_len + GEN_THREADS - 1) / GEN_THREADS);
     sq.rec_off = plan.rec_total;
     sq.cta_off = plan.cta_total;
@@ -704,7 +838,7 @@ void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u6
     plan.qs.push_back(sq);
 }
 
-struct SpanLayout { u64 words, groups, rec, rec2, cta, total; };
+struct SpanLayout { u64 words, groups, rec, rec2, cta, matches, total; };
 static SpanLayout span_layout(const SpanPlan &plan) {
     SpanLayout L;
     L.words = 0;
@@ -712,7 +846,8 @@ static SpanLayout span_layout(const SpanPlan &plan) {
     L.rec = align_up(L.groups + plan.groups_total * sizeof(u32), 256);
     L.rec2 = align_up(L.rec + plan.rec_total * sizeof(u64), 256);
     L.cta = align_up(L.rec2 + plan.rec_total * sizeof(u32), 256);
-    L.total = align_up(L.cta + plan.cta_total * sizeof(CtaRec), 256) + 256;
+    L.matches = align_up(L.cta + plan.cta_total * sizeof(CtaRec), 256);
+    L.total = align_up(L.matches + plan.match_total * sizeof(u64), 256) + 256;
     return L;
 }
 
@@ -732,7 +867,8 @@ int sa_span_is_literal(sa_index *ix, const u64 *d_lists, const u64 *offs, const 
 }
 
 int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, const SpanQuery *d_qs,
-                    SpanCounts *d_counts, void *d_scratch, float *dense_rows, u64 stride) {
+                    SpanCounts *d_counts, void *d_scratch, float *dense_rows, u64 stride,
+                    const TopkCtx *topk, u32 topk_row0) {
     const u32 Q = (u32)plan.qs.size();
     if (Q == 0) return SA_OK;
     SA_CHECK(plan.groups_total < 0xFFFFFFFFull && plan.words_total < 0xFFFFFFFFull, "slop query too large");
@@ -754,7 +890,21 @@ int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, cons
     a.n_docs = ix->n_docs;
     a.doc_base = ix->doc_base;
     SA_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)Q * sizeof(SpanCounts), ix->stream));
-    SA_CUDA(cudaMemsetAsync(dense_rows, 0, (size_t)Q * stride * sizeof(float), ix->stream));
+    if (topk) {
+        a.matches = (u64 *)(base + L.matches);
+        a.norm = ix->d_norm;
+        a.topk = *topk;
+        a.topk_row0 = topk_row0;
+        const u64 n_tiles = (ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS;
+        const u64 want = std::max<u64>(1, (u64)ix->num_sms * 16 / Q);
+        const u64 tiles_per_chunk = std::max<u64>(1, (n_tiles + want - 1) / want);
+        a.n_chunks = (u32)((n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+        a.docs_per_chunk = tiles_per_chunk * SA_TILE_DOCS;
+        // rows are addressed by absolute row (topk_row0 + q) in span_tiles_kernel
+        a.out = dense_rows - (u64)topk_row0 * stride;
+    } else {
+        SA_CUDA(cudaMemsetAsync(dense_rows, 0, (size_t)Q * stride * sizeof(float), ix->stream));
+    }
     KernelTimer t(ix, 2);
     if (plan.max_ctas) {
         dim3 grid(plan.max_ctas, Q);
@@ -794,9 +944,17 @@ int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, cons
     dim3 grid2((unsigned)std::max<u64>(1, std::min<u64>(want, budget)), Q);
     span_groups_kernel<<<grid2, SPAN_WARPS * 32, SPAN_WARPS * sizeof(WarpSpans), ix->stream>>>(a);
     SA_CUDA(cudaGetLastError());
-    t.stop();
     ix->stats.phrase_kernel_launches += 1;
     ix->stats.total_launches += 1;
+    if (topk) {
+        span_sorted_kernel<<<dim3(8, Q), GEN_THREADS, 0, ix->stream>>>(a);
+        SA_CUDA(cudaGetLastError());
+        span_tiles_kernel<<<dim3(a.n_chunks, Q), SA_TERM_THREADS, 0, ix->stream>>>(a);
+        SA_CUDA(cudaGetLastError());
+        ix->stats.phrase_kernel_launches += 2;
+        ix->stats.total_launches += 2;
+    }
+    t.stop();
     return SA_OK;
 }
 

@@ -18,19 +18,21 @@ struct SpanQuery {
     u64 s_off[SA_MAX_PHRASE_TERMS];     // sliced-list region of term t in the word arena
     u64 g_off[SA_MAX_PHRASE_TERMS];     // group-start region of term t in the u32 arena
     u64 s_cap[SA_MAX_PHRASE_TERMS];
+    u64 m_off;                          // match records (one per phase-2 iteration) of this query
 };
 
 struct SpanCounts {                      // written by phase 1, read by phase 2
     u32 n_sliced[SA_MAX_PHRASE_TERMS];
     u32 n_groups[SA_MAX_PHRASE_TERMS];
     u32 overflow;
+    u32 unsorted;                        // the match records are not in doc order (misaligned doc groups)
     u32 undefined;                       // span-table overflows the reference leaves undefined
 };
 
 // Host-side plan of a batch of span queries: descriptors + scratch layout.
 struct SpanPlan {
     std::vector<SpanQuery> qs;
-    u64 words_total = 0, groups_total = 0, rec_total = 0, cta_total = 0;
+    u64 words_total = 0, groups_total = 0, rec_total = 0, cta_total = 0, match_total = 0;
     u32 max_ctas = 0;
     u64 max_shortest = 0;
     bool any_literal = false;
@@ -40,10 +42,14 @@ struct SpanPlan {
 void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u64 *dir_offs, u32 n_terms,
                       u32 slop, float idf, bool literal);
 size_t sa_span_scratch_bytes(const SpanPlan &plan);
-// Enqueues the whole plan: raw span counts are ADDED into dense_rows[q * stride + doc] (the rows are
-// zeroed here).  d_qs: device copy of plan.qs; d_counts: SpanCounts[Q] (zeroed here).
+// Enqueues the whole plan.  d_qs: device copy of plan.qs; d_counts: SpanCounts[Q] (zeroed here).
+// topk != NULL (batched path): nothing is pre-zeroed; the matches become per-query records and one
+// tile pass writes the dense rows (zeros + BM25-scored matches, sa_ensure_norm must have run) and
+// collects the top-k candidates (rows topk_row0 + q).  topk == NULL: raw counts are ADDED into the
+// rows, which are zeroed here.
 int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, const SpanQuery *d_qs,
-                    SpanCounts *d_counts, void *d_scratch, float *dense_rows, u64 stride);
+                    SpanCounts *d_counts, void *d_scratch, float *dense_rows, u64 stride,
+                    const struct TopkCtx *topk = nullptr, u32 topk_row0 = 0);
 // One query, synchronously, into ix->dense row 0 (raw counts).
 int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *lens, const u64 *dir_offs,
                 uint32_t n_terms, uint32_t slop, bool literal, u32 *n_undefined);
