@@ -50,8 +50,11 @@ term_tile_kernel(const TermBatchArgs a) {
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
 
-    const u32 q = blockIdx.y;
-    const u32 tile = blockIdx.x;
+    // grid = (queries, tiles): consecutive CTAs work on the SAME tile of different queries, so at any
+    // moment an SM holds a mix of dense (issue-bound) and sparse (store-bound) terms, and the tile's
+    // norm sectors are shared in L2 by all queries of the launch
+    const u32 q = a.query_major ? blockIdx.y : blockIdx.x;
+    const u32 tile = a.query_major ? blockIdx.x : blockIdx.y;
     const TermQuery tq = a.queries[q];
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 *__restrict__ words = a.words + tq.word_off;
@@ -401,7 +404,10 @@ int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
         if (rc) return rc;
         a.norm = ix->d_norm;
     }
-    dim3 grid((unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS), n_queries);
+    const unsigned n_tiles = (unsigned)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    static const bool env_qmajor = getenv("SA_TERM_QUERY_MAJOR") && atoi(getenv("SA_TERM_QUERY_MAJOR")) != 0;
+    a.query_major = (env_qmajor || n_tiles > 65535) ? 1 : 0;
+    dim3 grid = a.query_major ? dim3(n_tiles, n_queries) : dim3(n_queries, n_tiles);
     dim3 block(SA_TERM_THREADS);
     KernelTimer t(ix, 0);
     if (a.mode == TERM_MODE_TF) {

@@ -37,6 +37,7 @@ struct TermBatchArgs {
     int filter;                 // apply the payload_slice filter
     int mode;
     u32 staged_norm_min_words;  // set by launch_term_batch
+    u32 query_major;            // grid layout (set by launch_term_batch): 1 = (tiles, queries), 0 = (queries, tiles)
     TopkCtx topk;
 };
 
