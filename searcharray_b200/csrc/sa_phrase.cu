@@ -319,11 +319,13 @@ phrase_kernel(const PhraseArgs a) {
     __shared__ u32 s_top[(PT / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
 
-    const u32 q = blockIdx.y;
+    // grid = (queries, chunks): neighbouring CTAs belong to different queries (see term_tile_kernel)
+    const u32 q = blockIdx.x;
+    const u32 chunk = blockIdx.y;
     const PhraseQuery &pq = a.queries[q];
     const u32 n_terms = pq.n_terms;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const u64 d0 = a.doc_base + (u64)blockIdx.x * a.docs_per_chunk;
+    const u64 d0 = a.doc_base + (u64)chunk * a.docs_per_chunk;
     const u64 dend = a.doc_base + a.n_docs;
     if (d0 >= dend) return;                    // (grid is sized so this does not happen)
     const u64 d1 = min(d0 + a.docs_per_chunk, dend);
@@ -457,7 +459,7 @@ phrase_kernel(const PhraseArgs a) {
     Bm25Params p = a.bm25;
     p.idf = pq.idf;
     const u32 row = a.topk_row0 + q;
-    const u32 tile0 = (u32)(((u64)blockIdx.x * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
     const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
     // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
     // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
@@ -516,7 +518,7 @@ phrase_kernel(const PhraseArgs a) {
 
 int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries) {
     if (n_queries == 0 || a.n_docs == 0) return SA_OK;
-    dim3 grid(a.n_chunks, n_queries);
+    dim3 grid(n_queries, a.n_chunks);
     KernelTimer t(ix, 2);
     phrase_kernel<<<grid, PT, 0, ix->stream>>>(a);
     SA_CUDA(cudaGetLastError());

@@ -696,7 +696,8 @@ span_tiles_kernel(const SpanArgs a) {
     __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
     __shared__ u32 s_top[(SA_TERM_THREADS / 32) * 8];
     __shared__ u32 s_ncand, s_tile_max;
-    const u32 q = blockIdx.y;
+    const u32 q = blockIdx.x;            // grid = (queries, chunks)
+    const u32 chunk = blockIdx.y;
     const SpanQuery &sq = a.queries[q];
     const unsigned tid = threadIdx.x;
     const u32 iters = a.counts[q].n_groups[0];
@@ -705,8 +706,8 @@ span_tiles_kernel(const SpanArgs a) {
     const u32 row = a.topk_row0 + q;
     float *out = a.out + (u64)row * a.out_stride;
     const u32 n_tiles = (u32)((a.n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
-    const u32 tile0 = (u32)(((u64)blockIdx.x * a.docs_per_chunk) / SA_TILE_DOCS);
-    const u32 tile1 = min(n_tiles, (u32)((((u64)blockIdx.x + 1) * a.docs_per_chunk) / SA_TILE_DOCS));
+    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = min(n_tiles, (u32)((((u64)chunk + 1) * a.docs_per_chunk) / SA_TILE_DOCS));
     // sorted records: cursor at the first record of this chunk (uniform bisect)
     u64 cur = 0;
     if (sorted) {
@@ -949,7 +950,7 @@ int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, cons
     if (topk) {
         span_sorted_kernel<<<dim3(8, Q), GEN_THREADS, 0, ix->stream>>>(a);
         SA_CUDA(cudaGetLastError());
-        span_tiles_kernel<<<dim3(a.n_chunks, Q), SA_TERM_THREADS, 0, ix->stream>>>(a);
+        span_tiles_kernel<<<dim3(Q, a.n_chunks), SA_TERM_THREADS, 0, ix->stream>>>(a);
         SA_CUDA(cudaGetLastError());
         ix->stats.phrase_kernel_launches += 2;
         ix->stats.total_launches += 2;
