@@ -1,6 +1,7 @@
 // sa_common.cuh -- shared definitions for libsearcharray_b200 (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -54,7 +55,9 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + (bytes >> 3) + 256;
+        // grow geometrically: cudaFree + cudaMalloc synchronise the device, so a buffer that creeps up
+        // query by query must not be reallocated on every new maximum
+        size_t want = std::max(bytes + (bytes >> 3), cap + (cap >> 1)) + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             sa_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));

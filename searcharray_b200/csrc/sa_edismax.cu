@@ -23,6 +23,7 @@
 //                        exactly (score desc, doc asc).
 #include <algorithm>
 #include <cmath>
+#include <functional>
 
 #include "sa_phrase.cuh"
 #include "sa_term.cuh"
@@ -48,6 +49,7 @@ struct sa_multi {
     bool f32_mode = false, has_qf = false;
     std::vector<std::vector<u64>> filt_offs, filt_lens;   // per field: last sa_multi_filter
     std::vector<u32> phrase_rows;        // per field: rows produced by the last sa_multi_phrases
+    std::vector<u64> filt_bound;         // per field: words reserved for filtered lists (0 = not computed yet)
     DevBuf cand, meta, keys;
     std::mutex mu;
 };
@@ -249,6 +251,7 @@ extern "C" int sa_multi_create(sa_index *const *fields, uint32_t n_fields, sa_mu
     m->filt_offs.resize(n_fields);
     m->filt_lens.resize(n_fields);
     m->phrase_rows.assign(n_fields, 0);
+    m->filt_bound.assign(n_fields, 0);
     cudaSetDevice(m->device);
     const u64 s = std::max<u64>(m->stride, SA_TILE_DOCS);
     bool ok = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -374,6 +377,19 @@ extern "C" int sa_multi_filter(sa_multi *m, uint32_t field, const uint32_t *term
         SA_CHECK(term_ids[t] == SA_NO_TERM || term_ids[t] < ix->n_terms, "term id %u out of range", term_ids[t]);
     FieldGuard fg(ix, m->stream);
     std::vector<u64> dfs;
+    if (m->filt_bound[field] == 0) {
+        // one allocation for any query: room for filtered copies of the longest lists a query could name
+        std::vector<u64> lens(ix->h_len);
+        const size_t top = std::min<size_t>(lens.size(), SA_MAX_PHRASE_TERMS);
+        std::partial_sort(lens.begin(), lens.begin() + top, lens.end(), std::greater<u64>());
+        u64 bound = 64;
+        for (size_t i = 0; i < top; i++) bound += lens[i] + 2;
+        m->filt_bound[field] = bound;
+    }
+    {
+        int rc0 = ix->filt.reserve(m->filt_bound[field] * sizeof(u64));
+        if (rc0) return rc0;
+    }
     int rc = sa_filter_terms_mask(ix, term_ids, n_terms, m->d_mask, 0, SA_ALL_BITS, false,
                                   m->filt_offs[field], m->filt_lens[field], &dfs);
     if (rc) return rc;

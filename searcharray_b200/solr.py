@@ -105,6 +105,20 @@ class _Multi:
             _lib._lib.sa_multi_destroy(handle)
 
 
+# optional per-call wall-clock accounting (tools / bench diagnostics): set to a dict to collect
+_TIMING = None
+
+
+def _timed(name, fn, *args):
+    if _TIMING is None:
+        return fn(*args)
+    import time
+    t0 = time.perf_counter()
+    rc = fn(*args)
+    _TIMING[name] = _TIMING.get(name, 0.0) + time.perf_counter() - t0
+    return rc
+
+
 _multis: Dict[tuple, _Multi] = {}
 _multis_lock = threading.Lock()
 
@@ -219,7 +233,7 @@ def _run_device(plan: _Plan) -> _Multi:
     n_matches = ctypes.c_uint64(0)
     a_nt, a_tid, a_idf = _u32(n_terms), _u32(tids if tids else [0]), _f32(idfs if idfs else [0])
     a_boost, a_hb, a_avgdl, a_k1, a_b, a_mm = _f32(boosts), _u32(has_boost), _f32(avgdl), _f32(k1), _f32(b), _u32(mms)
-    _lib.check(L.sa_multi_qf(multi.handle, 0 if plan.term_centric else 1, _lib.p_u32(a_nt), _lib.p_u32(a_tid),
+    _lib.check(_timed("qf", L.sa_multi_qf, multi.handle, 0 if plan.term_centric else 1, _lib.p_u32(a_nt), _lib.p_u32(a_tid),
                              _lib.p_f32(a_idf), _lib.p_f32(a_boost), _lib.p_u32(a_hb), _lib.p_f32(a_avgdl),
                              _lib.p_f32(a_k1), _lib.p_f32(a_b), _lib.p_u32(a_mm), float(plan.tie),
                              ctypes.byref(n_matches)))
@@ -246,7 +260,7 @@ def _run_device(plan: _Plan) -> _Multi:
         slot = {t: i for i, t in enumerate(uniq)}
         u_ids = _u32([arr._term_id(t) for t in uniq])
         dfs = np.zeros(len(uniq), dtype=np.uint64)
-        _lib.check(L.sa_multi_filter(multi.handle, fi, _lib.p_u32(u_ids), len(uniq), _lib.p_u64(dfs)))
+        _lib.check(_timed("filter", L.sa_multi_filter, multi.handle, fi, _lib.p_u32(u_ids), len(uniq), _lib.p_u64(dfs)))
         if comm is not None:
             dfs = comm.sum_u64(dfs)
         starts, slots, ids, p_idf = [0], [], [], []
@@ -259,7 +273,7 @@ def _run_device(plan: _Plan) -> _Multi:
             starts.append(len(slots))
             p_idf.append(compute_idf(arr.corpus_size, np.asarray([dfs[slot[t]] for t in ph])))
         a_st, a_sl, a_id, a_pi = _u32(starts), _u32(slots), _u32(ids), _f32(p_idf)
-        _lib.check(L.sa_multi_phrases(multi.handle, fi, len(rows), _lib.p_u32(a_st), _lib.p_u32(a_sl),
+        _lib.check(_timed("phrases", L.sa_multi_phrases, multi.handle, fi, len(rows), _lib.p_u32(a_st), _lib.p_u32(a_sl),
                                       _lib.p_u32(a_id), _lib.p_f32(a_pi), arr.avg_doc_length, sim.k1, sim.b))
     for name, items in phases:
         e_field, e_row, e_boost, e_hb = [], [], [], []
@@ -272,7 +286,7 @@ def _run_device(plan: _Plan) -> _Multi:
                 e_hb.append(0 if boost is None else 1)
         if e_field:
             a_f, a_r, a_bo, a_h = _u32(e_field), _u32(e_row), _f32(e_boost), _u32(e_hb)
-            _lib.check(L.sa_multi_add_phase(multi.handle, len(e_field), _lib.p_u32(a_f), _lib.p_u32(a_r),
+            _lib.check(_timed("add_phase", L.sa_multi_add_phase, multi.handle, len(e_field), _lib.p_u32(a_f), _lib.p_u32(a_r),
                                             _lib.p_f32(a_bo), _lib.p_u32(a_h)))
     return multi
 
@@ -361,7 +375,7 @@ def edismax_topk(frame: pd.DataFrame, q: str, qf: List[str], k: int = 10, mm: Op
     scores = np.empty(k, dtype=np.float64)
     with _multi_for(plan.arrays).lock:
         multi = _run_device(plan)
-        _lib.check(_lib.lib().sa_multi_topk(multi.handle, k, _lib.p_u32(docs),
+        _lib.check(_timed("topk", _lib.lib().sa_multi_topk, multi.handle, k, _lib.p_u32(docs),
                                             scores.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
     comm = plan.arrays[0].comm
     if comm is not None:                  # one all-gather of the per-shard top-k, merged on every rank
