@@ -371,8 +371,18 @@ def bench_ours(args, rank, world):
         peak, peak_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         pass
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this
+    # very workload (it cannot be measured live); null for any other configuration
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "term_kernel_traffic.json")))
+        if tj["config"] == {"n_docs": args.docs, "queries_per_step": Q, "n_gpus": world}:
+            traffic = float(tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"])
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "term_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
                 "avg_launch_ms": term_ms / launches_per_step, "launches_per_step": launches_per_step,
                 "topk_select_ms_per_step": stats.topk_kernel_ms / prof_steps,
