@@ -65,3 +65,24 @@ def test_mm_invalid(spec):
         solr.parse_min_should_match(10, spec)
     with pytest.raises(ValueError):
         psolr.parse_min_should_match(10, spec)
+
+
+def test_explain_strings_and_plan_on_host():
+    """The host half of searcharray_b200.solr (query parsing, phase lists, explain strings) needs
+    no GPU: compare the explain strings with the real reference's (golden)."""
+    import pandas as pd
+    from searcharray_b200 import SearchArray
+    from searcharray_b200 import solr as psolr
+    meta = json.load(open(os.path.join(GOLDEN, "edismax.json")))
+    frame = pd.DataFrame({"title": SearchArray.index(meta["title"]),
+                          "body": SearchArray.index(meta["body"]),
+                          "tag": SearchArray.index(meta["tag"], tokenizer=lower_one_token)})
+    for case in meta["cases"]:
+        kw = dict(case["kwargs"])
+        plan = psolr._Plan(frame, kw["q"], kw["qf"], kw.get("mm"), kw.get("pf"), kw.get("pf2"), kw.get("pf3"),
+                           kw.get("tie", 0.0), kw.get("q_op", "OR"), psolr.default_bm25)
+        assert plan.explain_qf() + plan.explain_phases() == case["explain"], case["name"]
+        assert plan.term_centric == (case["dtype"] == "float64")
+    assert psolr.parse_field_boosts(["title^2.5", "body"]) == {"title": 2.5, "body": None}
+    with pytest.raises(ValueError):
+        psolr.get_field(frame, "nope")

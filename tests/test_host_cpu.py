@@ -79,3 +79,69 @@ def test_shard_partition_covers_index(api):
         joined = np.concatenate([s.term_words(t) for s in shards])
         assert np.array_equal(joined, host.term_words(t))
     assert sum(s.n_docs for s in shards) == n
+
+
+def test_shard_comm_merge_topk_f64():
+    """ShardComm.merge_topk_f64 (the host merge of the all-gathered per-shard edismax top-k): fake a
+    2-rank all-gather and compare with a sort of the union."""
+    from searcharray_b200.shard import ShardComm
+    rng = np.random.default_rng(3)
+    k = 10
+    per_rank = []
+    for r in range(2):
+        n = 7 if r == 0 else 10
+        docs = np.full(k, 0xFFFFFFFF, dtype=np.uint32)
+        scores = np.zeros(k)
+        docs[:n] = rng.choice(1000, size=n, replace=False) + 1000 * r
+        scores[:n] = np.sort(rng.random(n))[::-1]
+        per_rank.append((docs, scores))
+    per_rank[1][1][2] = per_rank[0][1][1]          # a tie across shards: lower doc id first
+
+    class Fake(ShardComm):
+        """merge_topk_f64 gathers the doc ids first, then the score bit patterns."""
+
+        def __init__(self, rank):
+            super().__init__(None, rank, 2)
+            self.calls = 0
+
+        def allgather_u64(self, values):
+            assert np.array_equal(np.asarray(values, dtype=np.uint64),
+                                  per_rank[self.rank][self.calls].astype(np.uint64) if self.calls == 0
+                                  else per_rank[self.rank][1].view(np.uint64))
+            col = self.calls
+            self.calls += 1
+            return np.stack([per_rank[r][0].astype(np.uint64) if col == 0 else per_rank[r][1].view(np.uint64)
+                             for r in range(2)])
+
+    all_d = np.concatenate([p[0] for p in per_rank]).astype(np.int64)
+    all_s = np.concatenate([p[1] for p in per_rank])
+    keep = all_d != 0xFFFFFFFF
+    order = np.lexsort((all_d[keep], -all_s[keep]))[:k]
+    for rank in range(2):
+        d, s = Fake(rank).merge_topk_f64(*per_rank[rank], k)
+        assert np.array_equal(d, all_d[keep][order].astype(np.uint32))
+        assert np.array_equal(s, all_s[keep][order])
+
+
+def test_synth_title_field_and_edismax_queries():
+    """The second (title-like) field of the two-field corpus: same vocabulary, short docs, rarer
+    terms; shards of a 2-rank split concatenate to the 1-rank corpus; the body field is unchanged by
+    the field parameter."""
+    from searcharray_b200 import synth
+    n = 40_000
+    body = synth.SynthSpec(n)
+    title = synth.SynthSpec(n, field="title")
+    assert [t[0] for t in body.terms] == [t[0] for t in title.terms]
+    hb, _, _ = synth.generate_shard(body)
+    ht, lo, hi = synth.generate_shard(title)
+    assert (lo, hi) == (0, n) and ht.n_terms == hb.n_terms
+    assert 1 <= ht.doc_lens.min() and ht.doc_lens.max() <= 30 and 4 < ht.doc_lens.mean() < 8
+    assert len(ht.words) < len(hb.words) / 4
+    parts = [synth.generate_shard(title, r, 2) for r in range(2)]
+    assert parts[0][2] == parts[1][1]
+    for t in range(ht.n_terms):
+        assert np.array_equal(np.concatenate([p[0].term_words(t) for p in parts]), ht.term_words(t))
+    assert np.array_equal(np.concatenate([p[0].doc_lens for p in parts]), ht.doc_lens)
+    qs = synth.edismax_queries(body, 20)
+    assert all(2 <= len(q.split()) <= 5 for q in qs)
+    assert all(tok in body.term_index for q in qs for tok in q.split())
