@@ -218,6 +218,16 @@ int sa_op_popcount64_reduce(const uint64_t *words, uint64_t n, int device,
 /* bm25_score (bm25/bm25.pyx:28-41): in place over all n */
 int sa_op_bm25_score(float *tf_inout, const float *doc_lens, uint64_t n, float avg_doc_len,
                      float idf, float k1, float b, int device);
+/* The reference's other similarities (searcharray/similarity.py:41-89) evaluated on the device:
+ * SA_SIM_BM25_IMPACT -> float32[n] `tf / (tf + k1 * (1 - b + b * dl / avgdl))` (bm25_impact, :41-54; idf unused);
+ * SA_SIM_BM25_LEGACY -> float64[n] `idf * (tf * (k1 + 1)) / (...)` (bm25_legacy_similarity, :57-72);
+ * SA_SIM_CLASSIC     -> float64[n] `idf * sqrt(tf) * (1 / sqrt(dl))` (classic_similarity, :75-89; k1, b, avgdl unused).
+ * idf is the float64 scalar the caller computed the way the reference does; numpy's dtype promotion is reproduced. */
+#define SA_SIM_BM25_IMPACT 0
+#define SA_SIM_BM25_LEGACY 1
+#define SA_SIM_CLASSIC 2
+int sa_op_similarity(int kind, const float *term_freqs, const float *doc_lens, uint64_t n,
+                     double avg_doc_len, double idf, double k1, double b, int device, void *out);
 /* bigram_freqs (phrase/bigram_freqs.py:213-307): cont_rhs=1 -> Continuation.RHS else LHS.
  * ids/counts: per-doc matches (zero-count docs kept, quirk iv); next: continuation words.
  * Capacities: ids/counts >= min(n_lhs,n_rhs)*2, next >= 2*min(n_lhs, n_rhs)+2. */

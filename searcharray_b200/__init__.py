@@ -6,5 +6,6 @@ surface.  Host code is Python (numpy / pandas); the kernels are reached through 
 include/searcharray_b200.h via ctypes.  No PyTorch, no Triton, no CPU fallback.
 """
 from .postings import SearchArray, Terms, TermsDtype, ws_tokenizer  # noqa: F401
-from .similarity import Similarity, bm25_similarity, compute_idf, default_bm25  # noqa: F401
+from .similarity import (Similarity, bm25_similarity, bm25_impact, bm25_legacy_similarity,  # noqa: F401
+                         classic_similarity, compute_idf, default_bm25)
 from .indexing import HostIndex, TermDict, TermMissingError  # noqa: F401

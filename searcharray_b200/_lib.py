@@ -76,6 +76,8 @@ SIGNATURES = {
     "sa_multi_topk": (c_int, [P_void, c_u32, P_u32, ctypes.POINTER(ctypes.c_double)]),
     "sa_op_popcount64_reduce": (c_int, [P_u64, c_u64, c_int, P_u64, P_f32, P_u64]),
     "sa_op_bm25_score": (c_int, [P_f32, P_f32, c_u64, c_f32, c_f32, c_f32, c_f32, c_int]),
+    "sa_op_similarity": (c_int, [c_int, P_f32, P_f32, c_u64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                 ctypes.c_double, c_int, P_void]),
     "sa_op_bigram_freqs": (c_int, [P_u64, c_u64, P_u64, c_u64, c_int, c_int, P_u64, P_f32, P_u64, P_u64, P_u64]),
 }
 
