@@ -1,4 +1,4 @@
-// sa_term.cu -- the term-at-a-time BM25 scan (the headline kernel), v2.
+// sa_term.cu -- the term-at-a-time BM25 scan (the headline kernel).
 //
 // Replaces, fused into one launch per query batch:
 //   popcount64_reduce   searcharray/roaringish/popcount.pyx:212-237  (tf by doc)
@@ -6,27 +6,31 @@
 //   bm25_score          searcharray/bm25/bm25.pyx:11-41
 //
 // Design (B200).  The dense float32[N] score vector is cut into tiles of SA_TILE_DOCS docs; one
-// CTA owns one (tile, query) and builds the tile in 16 KB of shared memory:
+// CTA owns one (query, tile) and builds the tile in 32 KB of shared memory:
 //   1. the slice [lo,hi) of the term's posting words whose docs fall in the tile comes from the
 //      term's tile directory (two loads; built at upload for long lists) or, for short lists,
 //      from a warp-cooperative 32-ary search;
 //   2. the slice is streamed with coalesced 8-byte loads (4 windows in flight per thread).  Words
 //      are sorted by doc, so the words of one doc are adjacent: the thread holding the FIRST word
 //      of a doc ("head") adds the popcounts of the doc's run (neighbours via warp shuffle over
-//      overlapping 32-lane windows), gathers the doc's precomputed BM25 length norm (gathers
-//      issued back to back), evaluates tf/(tf+norm)*idf with individually rounded operations
-//      (bit-identical to the reference's x86-64 build) and stores the score into the shared
-//      tile.  No atomics, no work for docs that do not contain the term;
+//      overlapping 32-lane windows), takes the doc's precomputed BM25 length norm (a gather per
+//      pass, issued back to back; dense tiles stage the tile's norms with cp.async instead),
+//      evaluates tf/(tf+norm)*idf with individually rounded operations (bit-identical to the
+//      reference's x86-64 build) and stores the score into the shared tile.  No atomics, no work
+//      for docs that do not contain the term;
 //   3. the tile is flushed once with 16-byte streaming stores; while it passes through registers
 //      every score >= a running, provably valid lower bound of the k-th best score is appended to
 //      the query's top-k candidate list (sa_topk.cu), so the dense vector is never re-read.
-// HBM traffic = 8*W (words) + <= 32 B sectors holding the 4*df norms + 4*N (scores): the
-// algorithmic minimum of SURVEY.md section 8d.  v1 of this kernel (profiles/r1a_*) evaluated
-// BM25 for all 16 docs of every thread under divergence and was instruction-bound (47 % issue
-// utilisation at 21 % of the HBM roofline); v2 does work proportional to the postings.  A variant
-// staging the slice with TMA bulk copies (cp.async.bulk + mbarrier) was measured slower on every
-// df bucket (profiles/README.md): the scan is bound by instruction issue on dense terms and by the
-// dense 4N write otherwise, not by load latency.
+// The grid is (queries, tiles) -- the query index runs fastest -- so that the CTAs resident on an
+// SM at any time belong to MANY queries: dense terms (issue-bound CTAs) and sparse terms
+// (store-bound CTAs) overlap, and a tile's norm sectors are shared in L2 by all queries.  With the
+// tiles of one query back to back the same kernel was 17 % slower (profiles/README.md).
+// HBM traffic: 8*W (words) + the 32 B sectors holding the 4*df norms + 4*N (scores), less whatever
+// the queries of one launch share in L2.  History (profiles/): v1 evaluated BM25 for all 16 docs of
+// every thread under divergence with shared-memory atomics and was instruction-bound at 21 % of
+// the HBM roofline; variants that staged the postings with TMA bulk copies (cp.async.bulk +
+// mbarrier), wrote zeros straight to HBM for sparse tiles, or pinned the norm table in L2 measured
+// slower and were dropped.
 #include <algorithm>
 #include <type_traits>
 
