@@ -145,3 +145,20 @@ def test_synth_title_field_and_edismax_queries():
     qs = synth.edismax_queries(body, 20)
     assert all(2 <= len(q.split()) <= 5 for q in qs)
     assert all(tok in body.term_index for q in qs for tok in q.split())
+
+
+def test_pickle_round_trip_keeps_the_index_and_drops_device_state():
+    """reference test/test_search.py:62-73 (pickle round trip): the host index travels, device
+    handles never do (they are re-created lazily on first use)."""
+    import pickle
+    from searcharray_b200 import SearchArray
+    arr = SearchArray.index(["foo bar bar baz", "data2", "data3 bar", "bunny funny wunny"] * 5)
+    arr._shared["dev"] = object()                  # stand-in for a live device handle
+    clone = pickle.loads(pickle.dumps(arr))
+    assert clone._shared["dev"] is None
+    assert np.array_equal(clone.host.words, arr.host.words)
+    assert np.array_equal(clone.doc_lens, arr.doc_lens) and clone.avg_doc_length == arr.avg_doc_length
+    assert clone.term_dict.term_to_ids == arr.term_dict.term_to_ids
+    assert len(clone) == len(arr) and clone.corpus_size == arr.corpus_size
+    view = pickle.loads(pickle.dumps(arr[1::2]))
+    assert np.array_equal(view.rows, np.arange(len(arr))[1::2])
