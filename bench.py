@@ -158,6 +158,20 @@ def best_thread_count(one, term_ids, cores):
     return best
 
 
+def cold_cpu_qps(idx, one, term_ids, n=6):
+    """the reference's COLD path (`posns.clear_cache()` before each query, as
+    test_msmarco.py:362-379 does): tf by popcount and df by unique on every call.  One thread."""
+    sample = [int(t) for t in term_ids[:n]]
+    t0 = time.perf_counter()
+    for t in sample:
+        idx._df_cache.clear()
+        idx._tf_cache.clear()
+        one(t)
+    dt = time.perf_counter() - t0
+    return {"value": len(sample) / dt, "unit": "queries/s", "cores": 1,
+            "sample": f"{len(sample)} queries, tf/df caches cleared before each"}
+
+
 def run_cpu_sample(one, term_ids, threads):
     from concurrent.futures import ThreadPoolExecutor
     t0 = time.perf_counter()
@@ -188,6 +202,7 @@ def bench_reference(args, rank, world):
     for _ in range(args.steps):
         t += run_cpu_sample(one, sample, threads)
     qps = args.steps * len(sample) / t
+    cold = cold_cpu_qps(idx, one, sample)
     line = {
         "impl": "reference", "metric": "queries/sec (single-term BM25 + top-k) on 10M-doc synthetic MSMARCO",
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -196,7 +211,8 @@ def bench_reference(args, rank, world):
         "config": workload_config(args, len(sample)),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "host_cores": cores, "kind": "port",
                          "sample": f"{len(sample)} of the {args.queries} stratified term queries per step, "
-                                   f"ThreadPool({threads}) = fastest of the probed pool widths, warm tf cache"},
+                                   f"ThreadPool({threads}) = fastest of the probed pool widths, warm tf cache",
+                         "cold": cold},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -618,6 +634,10 @@ def bench_ours(args, rank, world):
                 bad += 1
             del ref
         cpu["gpu_topk_mismatches_in_16"] = bad
+        try:
+            cpu["cold"] = cold_cpu_qps(idx, one, sample)
+        except Exception as e:                      # informational; never fail the run for it
+            cpu["cold"] = {"error": repr(e)}
 
     verify = None
     if rank == 0 and args.verify:
