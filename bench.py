@@ -6,10 +6,10 @@
 
 Workload (config.workload): BASELINE.json configs[1] -- 10M-doc synthetic MSMARCO-shaped corpus
 (searcharray_b200/synth.py, seeded, generated as postings), single-term BM25.  One "step" = one
-pass over a batch of `--queries` stratified single-term queries: every query produces the dense
-float32[N] BM25 score vector in HBM and its exact top-k.  For N > 1 the 10M docs are sharded by
-contiguous doc-id range (strong scaling), one process per GPU, one ncclAllGather of the per-shard
-top-k per batch.
+pass over a batch of `--queries` (1,024) DISTINCT stratified single-term queries: every query
+produces the dense float32[N] BM25 score vector in HBM and its exact top-k.  For N > 1 the 10M docs
+are sharded by contiguous doc-id range (strong scaling), one process per GPU, one ncclAllGather of
+the per-shard top-k per batch.
 
   value : device-resident throughput -- query descriptors already in HBM, CUDA events on the
           library's stream around exactly K x sa_batch_execute (kernels + all-gather), max over ranks.
@@ -17,9 +17,13 @@ top-k per batch.
           (sa_score_batch_topk: H2D of the query descriptors, kernels, D2H of the top-k).
   e2e_dense : the literal `.score()` drop-in (sa_score_term), D2H of the dense float32[N] per query.
   roofline  : term_tile_kernel, algorithmic bytes 8*W + 4*df + 4*N per query over the
-          kernel's CUDA-event time, against MEASURED_PEAKS.json's hbm_gbs.
-  cpu_baseline : the oracle port (oracle/, the reference's algorithm in C + numpy, warm tf cache)
-          on the host cores, bounded sample.
+          kernel's CUDA-event time, against MEASURED_PEAKS.json's hbm_gbs; per-df-bucket fractions.
+  cpu_baseline : the reference's own `SearchArray.score` (oracle/_ref, `kind: "reference"`; the
+          oracle port when that build is absent) on the host cores, bounded sample, NO top-k
+          (the reference's stock call returns the dense vector; a top-k variant is reported apart).
+  verify : GPU top-k (docs AND score bits) of a sample of the step's queries against the CPU oracle.
+Extra blocks: `phrase` (configs[2]; rare-term and hard strata, B_phrase roofline), `phrase.slop2`
+(configs[3]), `bigram` (BASELINE.md's common x mid case), `edismax` (configs[4] shape).
 """
 import argparse
 import ctypes
@@ -44,18 +48,14 @@ def log(*a):
 
 
 # --------------------------------------------------------------------------- corpus
-def build_corpus(n_docs, rank, world):
+def build_corpus(n_docs, rank, world, field="body"):
     from searcharray_b200 import synth
-    spec = synth.SynthSpec(n_docs)
+    spec = synth.SynthSpec(n_docs, field=field)
     t0 = time.time()
     host, lo, hi = synth.generate_shard(spec, rank, world)
-    # global avg doc length: exact float64 mean over ALL blocks' doc_lens (cheap), as float32
-    total = 0.0
-    for b in range(synth.N_BLOCKS):
-        total += float(np.sum(synth.gen_doc_lens(n_docs, b), dtype=np.float64))
-    avgdl = np.float32(total / n_docs)
-    log(f"rank {rank}: generated docs [{lo},{hi}) {host.words.nbytes / 1e6:.0f} MB of postings "
-        f"in {time.time() - t0:.1f}s, avgdl={avgdl}")
+    avgdl = synth.global_avg_doc_length(spec)       # float32 of the exact global mean, same on every rank
+    log(f"rank {rank}: {field} docs [{lo},{hi}) {host.words.nbytes / 1e6:.0f} MB of postings, "
+        f"{host.n_terms} terms, in {time.time() - t0:.1f}s, avgdl={avgdl}")
     return spec, host, lo, hi, avgdl
 
 
@@ -68,6 +68,11 @@ def make_queries(spec, n_queries):
 def idf_of(n_docs, df):
     from searcharray_b200.similarity import compute_idf
     return np.asarray([compute_idf(n_docs, np.asarray([d])) for d in df], dtype=np.float32)
+
+
+def phrase_idf(n_docs, df, term_ids):
+    d = df[np.asarray(term_ids)].astype(np.float64)
+    return np.float32(np.sum(np.log(1 + (n_docs - d + 0.5) / (d + 0.5))))
 
 
 # --------------------------------------------------------------------------- clocks
@@ -98,8 +103,8 @@ class ClockSampler:
     def count_since(self, t_from):
         return sum(1 for t, _ in self.lines if t >= t_from)
 
-    def stop(self, t_from=0.0):
-        """Summary of the samples taken at or after t_from (the start of the timed region)."""
+    def stop(self, t_from=0.0, t_to=None):
+        """Summary of the samples taken in [t_from, t_to] (the timed regions)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -107,7 +112,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, ln in self.lines:
-            if t < t_from:
+            if t < t_from or (t_to is not None and t > t_to):
                 continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -125,63 +130,115 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU reference arm
-def cpu_reference_runner(host, avgdl, n_docs, k):
-    """The reference's CPU path for this workload, restated by the oracle port: warm tf/df caches
-    (PosnBitArray caches), as_dense + bm25_score over all N docs, np.argpartition top-k."""
-    from oracle import search as osearch
-    idx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
-                              avg_doc_length=avgdl, corpus_size=n_docs, cache=True)
+class CpuArm:
+    """The reference's CPU path for this workload: its own SearchArray.score (oracle/_ref, built from
+    /root/reference by oracle/build_ref.py) over the injected synthetic index; the oracle port
+    (oracle/search.py, the same algorithm restated in C + numpy) when that build is absent."""
 
-    def one(term_id):
-        scores = idx.score(int(term_id), k1=K1, b=B)
-        top = np.argpartition(scores, -k)[-k:]            # reference utils/sort.py:24
-        return top[np.argsort(-scores[top], kind="stable")]
-    return idx, one
+    def __init__(self, spec, host, avgdl, n_docs):
+        from oracle import ref_runner
+        self.spec, self.host = spec, host
+        self.names = [t[0] for t in spec.terms]
+        if ref_runner.available() and not os.environ.get("SA_BENCH_FORCE_PORT"):
+            self.kind = "reference"
+            self.arr = ref_runner.reference_array(host, avg_doc_length=avgdl, corpus_size=n_docs, names=self.names)
+            self.sim = ref_runner.bm25(K1, B)
+        else:
+            from oracle import search as osearch
+            self.kind = "port"
+            self.idx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
+                                           avg_doc_length=avgdl, corpus_size=n_docs, cache=True)
+
+    def score_term(self, term_id):
+        """SearchArray.score(term) (reference postings.py:652-680): the dense float32[N] vector."""
+        if self.kind == "reference":
+            return self.arr.score(self.names[int(term_id)], similarity=self.sim)
+        return self.idx.score(int(term_id), k1=K1, b=B)
+
+    def score_phrase(self, term_ids, slop=0):
+        if self.kind == "reference":
+            return self.arr.score([self.names[int(t)] for t in term_ids], similarity=self.sim, slop=slop)
+        return self.idx.score([int(t) for t in term_ids], k1=K1, b=B, slop=slop)
+
+    def warm(self, term_ids, threads=1):
+        """tf / df caches of these terms, like SearchArray.index(autowarm=True) -> posns.warm()
+        (reference middle_out.py:337-342) does at index time."""
+        def one(t):
+            if self.kind == "reference":
+                self.arr.docfreq(self.names[int(t)])
+                self.arr.posns.termfreqs(int(t))
+            else:
+                self.idx.docfreq(int(t))
+                self.idx.termfreqs(int(t))
+        uniq = [int(t) for t in np.unique(term_ids)]
+        if threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, uniq))
+        else:
+            for t in uniq:
+                one(t)
+
+    def clear_cache(self):
+        if self.kind == "reference":
+            self.arr.posns.clear_cache()
+        else:
+            self.idx._df_cache.clear()
+            self.idx._tf_cache.clear()
 
 
-def best_thread_count(one, term_ids, cores):
-    """The reference's loops release the GIL but every query allocates ~3 dense float32[N]
-    temporaries (np.zeros / as_dense / argpartition): on many-core hosts a full-width thread pool
-    thrashes the allocator and the memory bus.  Probe a few pool widths and keep the fastest, so
-    the baseline is the best the host can do, not a strawman."""
+def run_cpu_sample(fn, items, threads):
+    from concurrent.futures import ThreadPoolExecutor
+    t0 = time.perf_counter()
+    if threads == 1:
+        for t in items:
+            fn(t)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(fn, items))
+    return time.perf_counter() - t0
+
+
+def best_thread_count(fn, term_ids, cores):
+    """The reference's Cython loops release the GIL, so `.score` runs from a thread pool
+    (test_msmarco.py:483-507); every call allocates a dense float32[N], so wide pools contend on
+    the allocator / page faults.  Probe a few widths and keep the fastest: the baseline is the best
+    the host can do with the stock call."""
     best, best_qps = 1, 0.0
     for th in sorted({1, 4, 8, 16, 32, 64, cores}):
         if th > cores:
             continue
-        # at least one query per thread, or a wide pool is never actually exercised by the probe
-        probe = term_ids[:min(len(term_ids), max(24, th))]
-        dt = run_cpu_sample(one, probe, th)
+        probe = term_ids[:min(len(term_ids), max(32, 2 * th))]
+        dt = run_cpu_sample(fn, probe, th)
         qps = len(probe) / dt
         log(f"cpu probe: {th} threads -> {qps:.1f} qps")
         if qps > best_qps:
             best, best_qps = th, qps
-    return best
+    return best, best_qps
 
 
-def cold_cpu_qps(idx, one, term_ids, n=6):
+def cpu_topk(scores, k):
+    """A sane top-k over the reference's dense vector (score desc, doc asc; score > 0)."""
+    nz = np.flatnonzero(scores > 0)
+    if len(nz) > k:
+        part = np.argpartition(scores[nz], -k)[-k:]
+        thr = scores[nz][part].min()
+        nz = nz[scores[nz] >= thr]                      # keep ties so the doc-asc rule is exact
+    order = np.lexsort((nz, -scores[nz].astype(np.float64)))[:k]
+    return nz[order].astype(np.uint32), scores[nz[order]]
+
+
+def cold_cpu_qps(arm, term_ids, n=6):
     """the reference's COLD path (`posns.clear_cache()` before each query, as
     test_msmarco.py:362-379 does): tf by popcount and df by unique on every call.  One thread."""
     sample = [int(t) for t in term_ids[:n]]
     t0 = time.perf_counter()
     for t in sample:
-        idx._df_cache.clear()
-        idx._tf_cache.clear()
-        one(t)
+        arm.clear_cache()
+        arm.score_term(t)
     dt = time.perf_counter() - t0
     return {"value": len(sample) / dt, "unit": "queries/s", "cores": 1,
             "sample": f"{len(sample)} queries, tf/df caches cleared before each"}
-
-
-def run_cpu_sample(one, term_ids, threads):
-    from concurrent.futures import ThreadPoolExecutor
-    t0 = time.perf_counter()
-    if threads == 1:
-        for t in term_ids:
-            one(t)
-    else:
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(one, term_ids))
-    return time.perf_counter() - t0
 
 
 def bench_reference(args, rank, world):
@@ -190,28 +247,39 @@ def bench_reference(args, rank, world):
     spec, host, lo, hi, avgdl = build_corpus(args.docs, 0, 1)
     names, term_ids = make_queries(spec, args.queries)
     cores = os.cpu_count() or 1
-    idx, one = cpu_reference_runner(host, avgdl, args.docs, args.k)
-    sample = term_ids[:min(len(term_ids), args.ref_sample)]
-    for t in np.unique(term_ids):               # warm the tf/df caches like SearchArray.warm()
-        idx.docfreq(int(t))
-        idx.termfreqs(int(t))
-    threads = best_thread_count(one, sample, cores)
+    arm = CpuArm(spec, host, avgdl, args.docs)
+    t0 = time.time()
+    arm.warm(term_ids, threads=min(cores, 32))
+    log(f"reference arm ({arm.kind}): warmed tf/df caches of {len(np.unique(term_ids))} terms in {time.time() - t0:.1f}s")
+    threads, probe_qps = best_thread_count(arm.score_term, term_ids, cores)
+    # bounded sample: the whole --steps/--warmup run has to end within a few minutes
+    budget_s = args.ref_budget
+    per_step = int(probe_qps * budget_s / max(1, args.steps + args.warmup))
+    q_step = len(term_ids) if per_step >= len(term_ids) else max(64, per_step // 64 * 64)
+    sample = term_ids[:min(len(term_ids), q_step)]
     for _ in range(args.warmup):
-        run_cpu_sample(one, sample[:max(8, len(sample) // 8)], threads)
+        run_cpu_sample(arm.score_term, sample, threads)
     t = 0.0
     for _ in range(args.steps):
-        t += run_cpu_sample(one, sample, threads)
+        t += run_cpu_sample(arm.score_term, sample, threads)
     qps = args.steps * len(sample) / t
-    cold = cold_cpu_qps(idx, one, sample)
+    one_thread = len(sample[:32]) / run_cpu_sample(arm.score_term, sample[:32], 1)
+    tk = sample[:24]
+    topk_qps = len(tk) / run_cpu_sample(lambda q: cpu_topk(arm.score_term(q), args.k), tk, min(threads, 8))
+    cold = cold_cpu_qps(arm, sample)
     line = {
-        "impl": "reference", "metric": "queries/sec (single-term BM25 + top-k) on 10M-doc synthetic MSMARCO",
+        "impl": "reference", "metric": "queries/sec (single-term BM25 .score()) on 10M-doc synthetic MSMARCO",
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, len(sample)),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "host_cores": cores, "kind": "port",
-                         "sample": f"{len(sample)} of the {args.queries} stratified term queries per step, "
-                                   f"ThreadPool({threads}) = fastest of the probed pool widths, warm tf cache",
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "host_cores": cores, "kind": arm.kind,
+                         "sample": f"{len(sample)} of the {args.queries} stratified term queries per step, stock "
+                                   f"SearchArray.score (dense float32[N], no top-k), ThreadPool({threads}) = fastest "
+                                   f"of the probed pool widths, warm tf/df caches",
+                         "one_thread": {"value": one_thread, "unit": "queries/s"},
+                         "score_plus_topk": {"value": topk_qps, "unit": "queries/s",
+                                             "note": "score + flatnonzero/argpartition top-k, informational"},
                          "cold": cold},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -221,28 +289,47 @@ def bench_reference(args, rank, world):
 def workload_config(args, queries_per_step):
     return {"workload": "10M-doc synthetic MSMARCO, single-term BM25, top-%d (BASELINE configs[1])" % args.k,
             "n_docs": args.docs, "queries_per_step": queries_per_step, "k": args.k,
-            "corpus": "searcharray_b200.synth seed 20260924, doc_lens~clip(lognormal(3.9,.45),8,400), "
-                      "48 query terms over df/N in {3e-1..1e-4}",
+            "corpus": "searcharray_b200.synth seed 20260924, doc_lens~floor(clip(lognormal(3.9,.45),8,400)), "
+                      "1024 DISTINCT query terms over df/N in {3e-1..1e-4}, every term once per step",
             "sharding": "contiguous doc-id ranges, one process per GPU",
-            "cache": "inputs larger than L2: every step streams queries_per_step dense float32[N] vectors"}
+            "cache": "inputs larger than L2: every step streams its own posting lists (8 GB at 10M docs) and "
+                     "queries_per_step dense float32[N] vectors"}
 
 
 # --------------------------------------------------------------------------- our arm
-def bench_ours(args, rank, world):
-    from searcharray_b200 import _lib
-    from searcharray_b200.postings import DeviceIndex
-    L = _lib.lib()
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    spec, host, lo, hi, avgdl = build_corpus(args.docs, rank, world)
-    names, term_ids = make_queries(spec, args.queries)
-    dev = DeviceIndex(host, device=local_rank, doc_base=lo)
-    h = dev.handle
+class Ours:
+    """Thin harness around one shard's sa_index handle and the batch API."""
 
-    if world > 1:
-        # NCCL_DEBUG=VERSION (some images default to it) prints a banner on STDOUT, which would
-        # break the one-JSON-line contract
-        # ... and WARN still prints the version line.  Unset means silent; whatever level the user
-        # asked for goes to a file instead of stdout.
+    def __init__(self, args, rank, world):
+        from searcharray_b200 import _lib
+        from searcharray_b200.postings import DeviceIndex
+        self._lib = _lib
+        self.L = _lib.lib()
+        self.args, self.rank, self.world = args, rank, world
+        self.local_rank = int(os.environ.get("LOCAL_RANK", rank))
+        self.spec, self.host, self.lo, self.hi, self.avgdl = build_corpus(args.docs, rank, world)
+        t0 = time.time()
+        self.dev = DeviceIndex(self.host, device=self.local_rank, doc_base=self.lo)
+        log(f"rank {rank}: upload {time.time() - t0:.1f}s")
+        self.h = self.dev.handle
+        self.ms = ctypes.c_double(0)
+        self.n_over = ctypes.c_uint32(0)
+        if world > 1:
+            self._init_comm()
+        L, h = self.L, self.h
+        df = np.zeros(self.host.n_terms, dtype=np.uint64)
+        tmp = ctypes.c_uint64(0)
+        for t in range(self.host.n_terms):
+            _lib.check(L.sa_docfreq(h, t, ctypes.byref(tmp)))
+            df[t] = tmp.value
+        self.df_local = df.copy()
+        if world > 1:
+            _lib.check(L.sa_comm_allreduce_sum_u64(h, _lib.p_u64(df), len(df)))
+        self.df = df                       # GLOBAL document frequencies (idf must not depend on sharding)
+
+    def _init_comm(self):
+        _lib, L, h, rank, world = self._lib, self.L, self.h, self.rank, self.world
+        # NCCL_DEBUG=VERSION/WARN print a banner on STDOUT, which would break the one-JSON-line contract
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG", None)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sa_b200_nccl_%h_%p.log")
@@ -259,7 +346,7 @@ def bench_ours(args, rank, world):
         else:
             t_wait = time.time()
             while not os.path.exists(key):
-                if time.time() - t_wait > 600:
+                if time.time() - t_wait > 900:
                     raise RuntimeError("timed out waiting for rank 0's NCCL id")
                 time.sleep(0.05)
             with open(key, "rb") as f:
@@ -269,85 +356,144 @@ def bench_ours(args, rank, world):
         if rank == 0:
             os.remove(key)
 
-    def barrier():
-        if world > 1:
-            _lib.check(L.sa_comm_barrier(h))
+    def barrier(self):
+        if self.world > 1:
+            self._lib.check(self.L.sa_comm_barrier(self.h))
 
-    def max_over_ranks(x):
+    def max_over_ranks(self, x):
         v = ctypes.c_double(x)
-        if world > 1:
-            _lib.check(L.sa_comm_allreduce_max(h, ctypes.byref(v)))
+        if self.world > 1:
+            self._lib.check(self.L.sa_comm_allreduce_max(self.h, ctypes.byref(v)))
         return v.value
 
-    # global document frequencies (idf must use unsharded df)
-    df = np.zeros(host.n_terms, dtype=np.uint64)
-    tmp = ctypes.c_uint64(0)
-    for t in range(host.n_terms):
-        _lib.check(L.sa_docfreq(h, t, ctypes.byref(tmp)))
-        df[t] = tmp.value
-    if world > 1:
-        _lib.check(L.sa_comm_allreduce_sum_u64(h, _lib.p_u64(df), len(df)))
+    # ---- the batch API
+    def upload(self, terms, starts, idf, slop, k):
+        _lib = self._lib
+        _lib.check(self.L.sa_batch_upload(self.h, _lib.p_u32(terms), _lib.p_u32(starts), _lib.p_f32(idf),
+                                          len(starts) - 1, slop, float(self.avgdl), K1, B, k))
+
+    def execute(self):
+        self._lib.check(self.L.sa_batch_execute_allgather(self.h) if self.world > 1 else self.L.sa_batch_execute(self.h))
+
+    def download(self, docs, scores):
+        _lib = self._lib
+        fn = self.L.sa_batch_download_allgather if self.world > 1 else self.L.sa_batch_download
+        _lib.check(fn(self.h, _lib.p_u32(docs), _lib.p_f32(scores), ctypes.byref(self.n_over)))
+        return self.n_over.value
+
+    def timed_executes(self, steps):
+        """K x execute between CUDA events on the library's stream; max over ranks, in ms."""
+        _lib, L, h = self._lib, self.L, self.h
+        self.barrier()
+        _lib.check(L.sa_timer_start(h))
+        for _ in range(steps):
+            self.execute()
+        _lib.check(L.sa_timer_stop(h, ctypes.byref(self.ms)))
+        self.barrier()
+        return self.max_over_ranks(self.ms.value)
+
+    def stats(self):
+        st = self._lib.SaStats()
+        self._lib.check(self.L.sa_stats_get(self.h, ctypes.byref(st)))
+        return st
+
+    def profiled(self, steps):
+        """term / phrase kernel ms per step from per-launch CUDA events (async, resolved at the end)."""
+        _lib, L, h = self._lib, self.L, self.h
+        _lib.check(L.sa_set_profiling(h, 1))
+        _lib.check(L.sa_stats_reset(h))
+        for _ in range(steps):
+            self.execute()
+        st = self.stats()
+        _lib.check(L.sa_set_profiling(h, 0))
+        return st
+
+
+def peak_hbm():
+    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    return peak, src
+
+
+def committed_traffic(kernel, cfg):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this very
+    workload (it cannot be measured live); None for any other configuration."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        for ent in tj.get(kernel, []):
+            if ent["config"] == cfg:
+                return float(ent["dram_bytes_read_per_launch"] + ent["dram_bytes_write_per_launch"]), ent["source"]
+    except Exception:
+        pass
+    return None, None
+
+
+def oracle_topk_term(full, avgdl, idf, term_id, k):
+    """The oracle's top-k keys for one term query: sparse tf (popcount64_reduce) -> BM25 on the
+    matching docs (bm25.pyx:20-25, bit-identical to scoring all N: tf == 0 scores +0.0) -> top-k."""
+    from oracle import ops as oops, search as osearch
+    from searcharray_b200.shard import shard_topk_keys, unpack_keys
+    ids, tfs = osearch.termfreqs_sparse(full.term_words(term_id))
+    sc = tfs.copy()
+    oops.bm25_score(sc, full.doc_lens[ids.astype(np.int64)], avgdl, float(idf), K1, B)
+    return unpack_keys(shard_topk_keys(ids, sc, k))
+
+
+def topk_of_dense(dense, k):
+    d, s = cpu_topk(dense, k)
+    docs = np.full(k, 0xFFFFFFFF, dtype=np.uint32)
+    scores = np.zeros(k, dtype=np.float32)
+    docs[:len(d)] = d
+    scores[:len(s)] = s
+    return docs, scores
+
+
+def bench_ours(args, rank, world):
+    from searcharray_b200 import synth
+    o = Ours(args, rank, world)
+    _lib, L, h, host, spec, avgdl, df = o._lib, o.L, o.h, o.host, o.spec, o.avgdl, o.df
+    names, term_ids = make_queries(spec, args.queries)
     idf = idf_of(args.docs, df[term_ids])
     starts = np.arange(len(term_ids) + 1, dtype=np.uint32)
     Q, k = len(term_ids), args.k
     out_docs = np.empty((Q, k), dtype=np.uint32)
     out_scores = np.empty((Q, k), dtype=np.float32)
-    n_over = ctypes.c_uint32(0)
-
-    def upload():
-        _lib.check(L.sa_batch_upload(h, _lib.p_u32(term_ids), _lib.p_u32(starts), _lib.p_f32(idf), Q, 0,
-                                     float(avgdl), K1, B, k))
-
-    def execute():
-        _lib.check(L.sa_batch_execute_allgather(h) if world > 1 else L.sa_batch_execute(h))
-
-    def download():
-        if world > 1:
-            _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(out_docs), _lib.p_f32(out_scores),
-                                                     ctypes.byref(n_over)))
-        else:
-            _lib.check(L.sa_batch_download(h, _lib.p_u32(out_docs), _lib.p_f32(out_scores), ctypes.byref(n_over)))
-        return n_over.value
 
     def e2e_step():
-        upload()
-        execute()
-        return download()
+        o.upload(term_ids, starts, idf, 0, k)
+        o.execute()
+        return o.download(out_docs, out_scores)
 
     # ---- warm-up (>= 3 full steps); the clock sampler (nvidia-smi -lms) starts here so that it is
     #      already delivering samples when the timed region begins
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(o.local_rank)
     clocks.start()
     overflow = 0
     for _ in range(max(args.warmup, 3)):
         overflow += e2e_step()
 
     # ---- value: device-resident, K x execute between CUDA events on the library stream
-    stats = _lib.SaStats()
-    upload()
+    o.upload(term_ids, starts, idf, 0, k)
     _lib.check(L.sa_stats_reset(h))
-    barrier()
     t_timed = time.time()
-    _lib.check(L.sa_timer_start(h))
-    for _ in range(args.steps):
-        execute()
-    ms = ctypes.c_double(0)
-    _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
-    barrier()
-    dev_ms = max_over_ranks(ms.value)
-    _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
-    launches_value = int(stats.total_launches)
-    download()
+    dev_ms = o.timed_executes(args.steps)
+    launches_value = int(o.stats().total_launches)
+    o.download(out_docs, out_scores)
     value = args.steps * Q / (dev_ms / 1e3)
 
     # ---- e2e: host buffers in, top-k out, every step
-    barrier()
+    o.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         overflow += e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    o.barrier()
+    e2e_s = o.max_over_ranks(time.perf_counter() - t0)
     e2e = args.steps * Q / e2e_s
+    t_timed_end = time.time()
     # clocks: samples taken during the two timed regions (device-timed steps + e2e steps).  When those
     # are shorter than a few sampling periods (many GPUs, small shards) the same step is repeated,
     # untimed, for ~0.4 s so that the clocks under this load are still observed.
@@ -355,239 +501,199 @@ def bench_ours(args, rank, world):
     if clocks.count_since(t_timed) < 4:
         n_extra = int(min(2000, max(1, 0.4 / max(dev_ms / 1e3 / args.steps, 1e-5))))
         for _ in range(n_extra):
-            execute()
-        barrier()
-        download()
+            o.execute()
+        o.barrier()
+        o.download(out_docs, out_scores)
+        t_timed_end = time.time()
         clock_note = f"timed regions too short to sample: + {n_extra} untimed repeats of the same step"
-    clk = clocks.stop(t_timed)
+    clk = clocks.stop(t_timed, t_timed_end)
     clk["note"] = clock_note
-    h2d = int(term_ids.nbytes + starts.nbytes + idf.nbytes + Q * 24)     # + TermQuery descriptors
+    h2d = int(term_ids.nbytes + starts.nbytes + idf.nbytes + Q * 32)     # + TermQuery descriptors
     d2h = int(Q * k * 8 + Q * 4)
 
     # ---- roofline of the dominant kernel (per-launch CUDA events, async)
     W = host.term_lengths[term_ids].astype(np.float64)
-    dfl = np.zeros(host.n_terms, dtype=np.float64)
-    for t in range(host.n_terms):
-        _lib.check(L.sa_docfreq(h, t, ctypes.byref(tmp)))
-        dfl[t] = tmp.value
-    alg_bytes_step = float(np.sum(8.0 * W + 4.0 * dfl[term_ids] + 4.0 * host.n_docs))
-    _lib.check(L.sa_set_profiling(h, 1))
-    _lib.check(L.sa_stats_reset(h))
+    dfl = o.df_local.astype(np.float64)
+    alg_q = 8.0 * W + 4.0 * dfl[term_ids] + 4.0 * host.n_docs          # per query, this shard
     prof_steps = min(args.steps, 5)
-    for _ in range(prof_steps):
-        execute()
-    _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
-    _lib.check(L.sa_set_profiling(h, 0))
-    term_ms = stats.term_kernel_ms / prof_steps
-    launches_per_step = stats.term_kernel_launches / prof_steps
-    achieved = alg_bytes_step / (term_ms / 1e3) / 1e9
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak, peak_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    except Exception:
-        pass
-    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this
-    # very workload (it cannot be measured live); null for any other configuration
-    traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "term_kernel_traffic.json")))
-        if tj["config"] == {"n_docs": args.docs, "queries_per_step": Q, "n_gpus": world}:
-            traffic = float(tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"])
-            traffic_src = tj["source"]
-    except Exception:
-        pass
+    st = o.profiled(prof_steps)
+    term_ms = st.term_kernel_ms / prof_steps
+    launches_per_step = st.term_kernel_launches / prof_steps
+    achieved = float(alg_q.sum()) / (term_ms / 1e3) / 1e9
+    peak, peak_src = peak_hbm()
+    traffic, traffic_src = committed_traffic("term_tile_kernel", {"n_docs": args.docs, "queries_per_step": Q, "n_gpus": world})
     roofline = {"bound": "hbm", "kernel": "term_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_step / launches_per_step,
+                "algorithmic_bytes_per_launch": float(alg_q.sum()) / launches_per_step,
+                "algorithmic_bytes": "8*W + 4*df + 4*N per query (SURVEY 8d), summed over the launch's queries",
                 "avg_launch_ms": term_ms / launches_per_step, "launches_per_step": launches_per_step,
-                "topk_select_ms_per_step": stats.topk_kernel_ms / prof_steps,
+                "topk_select_ms_per_step": st.topk_kernel_ms / prof_steps,
                 "kernel_share_of_step": term_ms / (dev_ms / args.steps)}
+    # per-df-bucket fractions: the same kernel over the queries of ONE bucket at a time
+    buckets = []
+    qb = np.asarray([spec.terms[t][2] for t in term_ids])
+    for bi, p in enumerate(synth.DF_BUCKETS):
+        sel = np.flatnonzero(qb == bi)
+        if len(sel) == 0:
+            continue
+        o.upload(np.ascontiguousarray(term_ids[sel]), np.arange(len(sel) + 1, dtype=np.uint32),
+                 np.ascontiguousarray(idf[sel]), 0, k)
+        for _ in range(2):
+            o.execute()
+        stb = o.profiled(3)
+        ms_b = stb.term_kernel_ms / 3
+        buckets.append({"df_over_n": p, "queries": int(len(sel)), "us_per_query": 1e3 * ms_b / len(sel),
+                        "achieved": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9,
+                        "frac": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9 / peak})
+    roofline["by_df_bucket"] = buckets
+    o.upload(term_ids, starts, idf, 0, k)
 
-    # ---- phrase workload (BASELINE configs[2]: 4-term phrase, slop 0) as an extra block
+    # ---- verify: GPU top-k (docs AND score bits) against the oracle, rank 0 holds the FULL corpus
+    verify = None
+    n_verify = args.verify if args.verify >= 0 else (48 if world == 1 else 16)
+    full = None
+    if n_verify:
+        o.execute()
+        o.download(out_docs, out_scores)
+        if rank == 0:
+            full = host if world == 1 else synth.generate_shard(spec, 0, 1)[0]
+            step = max(1, Q // n_verify)
+            checked, bad = 0, 0
+            for qi in list(range(0, Q, step))[:n_verify]:
+                wd, ws = oracle_topk_term(full, avgdl, idf[qi], int(term_ids[qi]), k)
+                checked += 1
+                if not (np.array_equal(wd, out_docs[qi]) and
+                        np.array_equal(ws.view(np.uint32), out_scores[qi].view(np.uint32))):
+                    bad += 1
+            verify = {"term": {"queries_checked": checked, "mismatches": bad,
+                               "what": "global top-%d doc ids and score bits vs the CPU oracle" % k}}
+            log("verify term:", verify["term"])
+
+    # ---- phrase workloads (BASELINE configs[2] and [3]) as extra blocks
     phrase = None
-    if args.phrase_queries > 0:
-        from searcharray_b200 import synth
-        pq_names = synth.phrase_queries(spec, args.phrase_queries)
-        p_terms = np.asarray([spec.term_index[t] for ph in pq_names for t in ph], dtype=np.uint32)
-        p_starts = np.arange(0, 4 * len(pq_names) + 1, 4, dtype=np.uint32)
-        p_idf = np.asarray([float(np.sum(np.log(1 + (args.docs - df[[spec.term_index[t] for t in ph]].astype(np.float64) + 0.5)
-                                                / (df[[spec.term_index[t] for t in ph]].astype(np.float64) + 0.5))))
-                            for ph in pq_names], dtype=np.float32)
-        PQ = len(pq_names)
+    bigram = None
+    cpu_arm = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_arm = CpuArm(spec, host, avgdl, args.docs)
+
+    def phrase_batch(queries, slop):
+        ids = [[spec.term_index[t] for t in ph] for ph in queries]
+        p_terms = np.asarray([t for ph in ids for t in ph], dtype=np.uint32)
+        p_starts = np.concatenate(([0], np.cumsum([len(ph) for ph in ids]))).astype(np.uint32)
+        p_idf = np.asarray([phrase_idf(args.docs, df, ph) for ph in ids], dtype=np.float32)
+        return ids, p_terms, p_starts, p_idf
+
+    def phrase_block(queries, slop, label, with_roofline):
+        """One batched pass family of phrase queries with `slop`: device-timed steps, the same steps
+        end to end (upload + execute + top-k download), B_phrase roofline, parity sample."""
+        ids, p_terms, p_starts, p_idf = phrase_batch(queries, slop)
+        PQ = len(queries)
         p_docs = np.empty((PQ, k), dtype=np.uint32)
         p_scores = np.empty((PQ, k), dtype=np.float32)
+        p_redo = 0
+        for _ in range(3):
+            o.upload(p_terms, p_starts, p_idf, slop, k); o.execute(); p_redo += o.download(p_docs, p_scores)
+        o.upload(p_terms, p_starts, p_idf, slop, k)
+        p_steps = max(2, args.steps)
+        p_ms = o.timed_executes(p_steps)
+        _lib.check(L.sa_stats_reset(h))
+        o.execute()
+        o.download(p_docs, p_scores)
+        st1 = o.stats()
+        o.barrier()
+        t0 = time.perf_counter()
+        for _ in range(p_steps):
+            o.upload(p_terms, p_starts, p_idf, slop, k); o.execute(); p_redo += o.download(p_docs, p_scores)
+        o.barrier()
+        p_e2e_s = o.max_over_ranks(time.perf_counter() - t0)
+        Wp = np.asarray([float(np.sum(host.term_lengths[ph])) for ph in ids])
+        blk = {"workload": label, "queries_per_step": PQ, "distinct_queries": len({tuple(q) for q in queries}),
+               "value": p_steps * PQ / (p_ms / 1e3), "unit": "queries/s", "ms_per_step": p_ms / p_steps,
+               "e2e": {"value": p_steps * PQ / p_e2e_s, "unit": "queries/s"}, "repairs": int(p_redo),
+               "queries_with_matches": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF)),
+               "mean_words_per_query_this_shard": float(np.mean(Wp)),
+               "min_list_words_mean": float(np.mean([np.min(host.term_lengths[ph]) for ph in ids]))}
+        if with_roofline:
+            stp = o.profiled(min(p_steps, 3))
+            k_ms = stp.phrase_kernel_ms / min(p_steps, 3)
+            alg = 8.0 * float(Wp.sum()) + 16.0 * st1.phrase_cont_words + 4.0 * host.n_docs * PQ + 4.0 * st1.phrase_matched_docs
+            tr, tr_src = committed_traffic("phrase_kernel", {"n_docs": args.docs, "queries_per_step": PQ, "n_gpus": world,
+                                                            "workload": label})
+            blk["roofline"] = {"bound": "hbm", "kernel": "phrase kernels (slop 0)", "achieved": alg / (k_ms / 1e3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peak,
+                               "traffic": tr, "traffic_source": tr_src,
+                               "algorithmic_bytes": "B_phrase = 8*sum(W) + 16*sum(C_s) + 4*N + 4*M (SURVEY 8d)",
+                               "algorithmic_bytes_per_step": alg, "sum_W_words": float(Wp.sum()),
+                               "sum_C_words": int(st1.phrase_cont_words), "matched_docs": int(st1.phrase_matched_docs),
+                               "kernel_ms_per_step": k_ms, "kernel_share_of_step": k_ms / (p_ms / p_steps),
+                               "note": "lists that a search skips are still credited: a fraction above 1 means the "
+                                       "kernel read less than B_phrase"}
+        # parity sample against the CPU arm's dense vector (score bits and doc ids of the top-k)
+        if cpu_arm is not None and n_verify:
+            nck = min(args.verify_phrases, PQ)
+            stepq = max(1, PQ // nck)
+            bad, t_cpu = 0, 0.0
+            for qi in list(range(0, PQ, stepq))[:nck]:
+                t0 = time.perf_counter()
+                dense = cpu_arm.score_phrase(ids[qi], slop=slop)
+                t_cpu += time.perf_counter() - t0
+                wd, ws = topk_of_dense(dense, k)
+                if not (np.array_equal(wd, p_docs[qi]) and np.array_equal(ws.view(np.uint32), p_scores[qi].view(np.uint32))):
+                    bad += 1
+            blk["verify"] = {"queries_checked": nck, "mismatches": bad,
+                             "what": "top-%d doc ids and score bits vs the CPU %s's dense .score()" % (k, cpu_arm.kind)}
+            blk["cpu_baseline"] = {"kind": cpu_arm.kind, "cores": 1, "value": nck / t_cpu, "unit": "queries/s",
+                                   "sample": f"{nck} of the step's queries, SearchArray.score(phrase, slop={slop}), one thread"}
+            log(label, "verify:", blk["verify"], "cpu q/s: %.1f" % (nck / t_cpu))
+        return blk
 
-        Wp = np.asarray([[host.term_lengths[spec.term_index[t]] for t in ph] for ph in pq_names], dtype=np.float64)
-
-        def phrase_block(slop):
-            """One batched pass family of the PQ phrase queries with `slop`: device-timed steps, then the
-            same steps end to end (upload + execute + top-k download)."""
-            def p_upload():
-                _lib.check(L.sa_batch_upload(h, _lib.p_u32(p_terms), _lib.p_u32(p_starts), _lib.p_f32(p_idf), PQ, slop,
-                                             float(avgdl), K1, B, k))
-
-            def p_download():
-                if world > 1:
-                    _lib.check(L.sa_batch_download_allgather(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
-                else:
-                    _lib.check(L.sa_batch_download(h, _lib.p_u32(p_docs), _lib.p_f32(p_scores), ctypes.byref(n_over)))
-                return n_over.value
-
-            p_redo = 0
-            for _ in range(3):
-                p_upload(); execute(); p_redo += p_download()
-            p_upload()
-            _lib.check(L.sa_stats_reset(h))
-            barrier()
-            _lib.check(L.sa_timer_start(h))
-            p_steps = max(2, args.steps)
-            for _ in range(p_steps):
-                execute()
-            _lib.check(L.sa_timer_stop(h, ctypes.byref(ms)))
-            barrier()
-            p_ms = max_over_ranks(ms.value)
-            p_download()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(p_steps):
-                p_upload(); execute(); p_redo += p_download()
-            barrier()
-            p_e2e_s = max_over_ranks(time.perf_counter() - t0)
-            return {"queries_per_step": PQ, "value": p_steps * PQ / (p_ms / 1e3), "unit": "queries/s",
-                    "ms_per_step": p_ms / p_steps,
-                    "e2e": {"value": p_steps * PQ / p_e2e_s, "unit": "queries/s"},
-                    "repairs": int(p_redo),
-                    "matches_in_top1": int(np.sum(p_docs[:, 0] != 0xFFFFFFFF))}
-
-        phrase = {"workload": "4-term phrase, slop 0 (BASELINE configs[2]), planted phrases, top-%d" % k}
-        phrase.update(phrase_block(0))
-        phrase["mean_words_per_query_this_shard"] = float(np.mean(np.sum(Wp, axis=1)))
-        phrase["min_list_words_mean"] = float(np.mean(np.min(Wp, axis=1)))
-        slop2_batch = None
+    if args.phrase_queries > 0:
+        pq_all = synth.phrase_queries(spec, args.phrase_queries)
+        kinds = synth.phrase_kinds(spec, pq_all)
+        phrase = phrase_block(pq_all, 0, "4-term phrase, slop 0 (BASELINE configs[2]): 3/4 with one rare term "
+                              "(df/N <= 1e-3), 1/4 'hard' (all df/N >= 1e-2), planted + natural matches, top-%d" % k, True)
+        rare_q = [q for q, kd in zip(pq_all, kinds) if kd == "rare"]
+        hard_q = [q for q, kd in zip(pq_all, kinds) if kd == "hard"]
+        if rare_q and hard_q:
+            phrase["rare_only"] = phrase_block(rare_q, 0, "4-term phrase, slop 0, rare-term stratum", True)
+            phrase["hard_only"] = phrase_block(hard_q, 0, "4-term phrase, slop 0, hard stratum (all df/N >= 1e-2)", True)
         if args.slop_queries > 0:
-            slop2_batch = {"workload": "4-term phrase, slop 2 (BASELINE configs[3]), same batched top-%d API" % k}
-            slop2_batch.update(phrase_block(2))
-        # slop = 2 (BASELINE configs[3]) goes through the per-query C-ABI call: span search is
-        # latency/branch bound (SURVEY 8d: informational, no roofline expectation)
+            phrase["slop2"] = phrase_block(pq_all[:args.slop_queries], 2,
+                                           "4-term phrase, slop 2 (BASELINE configs[3]), same batched top-%d API" % k, False)
+        bq = synth.bigram_queries(spec, args.bigram_queries)
+        if bq:
+            bigram = phrase_block(bq, 0, "bigram common (df/N 3e-1) x mid (df/N 3e-2), slop 0 (BASELINE.md's 4.5M x 0.45M-word "
+                                  "case), top-%d" % k, True)
+        # slop = 2 through the per-query C-ABI call (the .score(..., slop=2) drop-in, dense vector to the host)
         if rank == 0 and world == 1 and args.slop_queries > 0:
             from searcharray_b200.postings import _pool
+            ids, p_terms, p_starts, p_idf = phrase_batch(pq_all[:16], 2)
             out = _pool.empty_f32(host.n_docs)
-            ns = min(args.slop_queries, PQ)
             _lib.check(L.sa_set_profiling(h, 1))
             _lib.check(L.sa_stats_reset(h))
             matched, dt = 0, 0.0
-            for i in range(ns):
-                tids = np.ascontiguousarray(p_terms[4 * i:4 * i + 4])
+            for i, ph in enumerate(ids):
+                tids = np.ascontiguousarray(ph, dtype=np.uint32)
                 t0 = time.perf_counter()
-                _lib.check(L.sa_score_phrase(h, _lib.p_u32(tids), 4, 2, float(p_idf[i]), float(avgdl), K1, B, 0,
+                _lib.check(L.sa_score_phrase(h, _lib.p_u32(tids), len(tids), 2, float(p_idf[i]), float(avgdl), K1, B, 0,
                                              _lib.ALL_BITS, _lib.p_f32(out)))
                 dt += time.perf_counter() - t0
                 matched += int(np.count_nonzero(out))
-            _lib.check(L.sa_stats_get(h, ctypes.byref(stats)))
+            stq = o.stats()
             _lib.check(L.sa_set_profiling(h, 0))
             phrase["slop2_dense"] = {"workload": "4-term phrase, slop 2, sa_score_phrase per query (the .score() drop-in), "
-                                                 "dense float32[N] to the host", "queries": ns,
-                                     "e2e": {"value": ns / dt, "unit": "queries/s"},
-                                     "kernel_ms_per_query": stats.phrase_kernel_ms / ns,
-                                     "mean_matching_docs": matched / ns}
-        if slop2_batch is not None:
-            phrase["slop2"] = slop2_batch
-        # CPU side of the phrase workload: the oracle port, a few queries (each is 50-500 ms)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            from oracle import search as osearch
-            oidx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
-                                       avg_doc_length=avgdl, corpus_size=args.docs, cache=True)
-            nsamp = min(8, PQ)
-            t0 = time.perf_counter()
-            for i in range(nsamp):
-                oidx.score([int(x) for x in p_terms[4 * i:4 * i + 4]], k1=K1, b=B)
-            dt0 = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            nslop = min(2, PQ)
-            for i in range(nslop):
-                oidx.score([int(x) for x in p_terms[4 * i:4 * i + 4]], k1=K1, b=B, slop=2)
-            dt2 = time.perf_counter() - t0
-            phrase["cpu_baseline"] = {"kind": "port", "cores": 1, "slop0_queries_per_s": nsamp / dt0,
-                                      "slop2_queries_per_s": nslop / dt2,
-                                      "sample": f"{nsamp} slop-0 and {nslop} slop-2 queries of the step, one thread"}
-        upload()          # restore the term batch for the sections below
+                                                 "dense float32[N] to the host", "queries": len(ids),
+                                     "e2e": {"value": len(ids) / dt, "unit": "queries/s"},
+                                     "kernel_ms_per_query": stq.phrase_kernel_ms / len(ids),
+                                     "mean_matching_docs": matched / len(ids)}
+        o.upload(term_ids, starts, idf, 0, k)          # restore the term batch for the sections below
 
     # ---- edismax (the shape of BASELINE configs[4], on this run's corpus size): two fields, mixed
-    #      2-5 term queries, qf + pf + pf2 + pf3, mm=2, tie=0.3 (reference test_msmarco.py:436-443);
-    #      per query: sa_multi_* calls from the host mirror, top-k back (all-gathered over the shards)
+    #      2-5 term queries, qf + pf + pf2 + pf3, mm=2, tie=0.3 (reference test_msmarco.py:436-443)
     edis = None
     if args.edismax_queries > 0:
-        import pandas as pd
-        from searcharray_b200 import SearchArray, solr, synth
-        from searcharray_b200.shard import ShardComm
-        t0 = time.time()
-        tspec = synth.SynthSpec(args.docs, field="title")
-        thost, _, _ = synth.generate_shard(tspec, rank, world)
-        ttotal = 0.0
-        for blk in range(synth.N_BLOCKS):
-            ttotal += float(np.sum(synth.gen_doc_lens(args.docs, blk, "title"), dtype=np.float64))
-        t_avgdl = np.float32(ttotal / args.docs)
-        comm = ShardComm(h, rank, world)
-        body = SearchArray.from_host_index(host, device=local_rank, doc_base=lo, corpus_size=args.docs,
-                                           avg_doc_length=avgdl, global_df=df, comm=comm)
-        body._shared["dev"] = dev                      # the body shard is already in HBM
-        title = SearchArray.from_host_index(thost, device=local_rank, doc_base=lo, corpus_size=args.docs,
-                                            avg_doc_length=t_avgdl, comm=comm)
-        tdev = title._device()
-        tdf = np.zeros(thost.n_terms, dtype=np.uint64)
-        for t in range(thost.n_terms):
-            _lib.check(L.sa_docfreq(tdev.handle, t, ctypes.byref(tmp)))
-            tdf[t] = tmp.value
-        title.global_df = comm.sum_u64(tdf)
-        frame = pd.DataFrame({"title": title, "body": body})
-        log(f"edismax: title field {thost.words.nbytes / 1e6:.0f} MB of postings, avgdl={t_avgdl}, "
-            f"set-up {time.time() - t0:.1f}s")
-        eq = synth.edismax_queries(spec, args.edismax_queries)
-        ekw = dict(qf=["title^1.0", "body^0.5"], pf=["body"], pf2=["body"], pf3=["body"], mm=2, tie=0.3)
-        for qtext in eq[:3]:
-            solr.edismax_topk(frame, qtext, k=k, **ekw)
-        barrier()
-        solr._TIMING = {}
-        t0 = time.perf_counter()
-        hits = 0
-        for qtext in eq:
-            d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
-            hits += int(d_[0] != 0xFFFFFFFF)
-        barrier()
-        e_s = max_over_ranks(time.perf_counter() - t0)
-        call_ms = {kk: 1e3 * vv / len(eq) for kk, vv in solr._TIMING.items()}
-        solr._TIMING = None
-        edis = {"workload": "two-field edismax (title^1.0 body^0.5, pf/pf2/pf3 on body, mm=2, tie=0.3), mixed 2-5 term "
-                            "queries, exact float64 top-%d, per-query host-driven sa_multi_* calls" % k,
-                "queries": len(eq), "e2e": {"value": len(eq) / e_s, "unit": "queries/s"},
-                "ms_per_query": 1e3 * e_s / len(eq), "queries_with_hits": hits,
-                "ms_per_query_by_call": call_ms}
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            from oracle import search as osearch, solr as osolr
-            ofields = {}
-            for name, hidx, adl in (("title", thost, t_avgdl), ("body", host, avgdl)):
-                oi = osearch.OracleIndex({t: hidx.term_words(t) for t in range(hidx.n_terms)}, hidx.doc_lens,
-                                         avg_doc_length=adl, corpus_size=args.docs, cache=True)
-                ofields[name] = osolr.OracleField(oi, hidx.term_dict.term_to_ids)
-            nq = min(2, len(eq))
-            t0 = time.perf_counter()
-            bad = 0
-            for qtext in eq[:nq]:
-                want = osolr.edismax(ofields, qtext, **ekw)
-                d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
-                order = np.lexsort((np.arange(len(want)), -want))[:k]
-                order = order[want[order] > 0]
-                if not (np.array_equal(d_[:len(order)], order.astype(np.uint32)) and
-                        np.allclose(s_[:len(order)], want[order], rtol=1e-5, atol=0)):
-                    bad += 1
-            dt = time.perf_counter() - t0
-            edis["cpu_baseline"] = {"kind": "port", "cores": 1, "value": nq / dt, "unit": "queries/s",
-                                    "sample": f"{nq} of the queries, oracle port of solr.py (includes the GPU "
-                                              "re-run used for the parity check, negligible)",
-                                    "gpu_topk_mismatches": bad}
-        upload()          # restore the term batch for the sections below
-        del frame, title, tdev
+        edis = edismax_block(args, o, cpu_arm)
+        o.upload(term_ids, starts, idf, 0, k)
 
     # ---- e2e_dense: the literal .score() drop-in, dense float32[N] to the host per query
     e2e_dense = None
@@ -605,57 +711,47 @@ def bench_ours(args, rank, world):
         dt = time.perf_counter() - t0
         e2e_dense = {"value": nd / dt, "unit": "queries/s", "d2h_bytes_per_query": int(host.n_docs * 4),
                      "note": "SearchArray.score drop-in: one sa_score_term call per query, pinned result vector"}
+        # dense parity at the BASELINE size: one term per df bucket, the whole float32[N] bit for bit
+        if cpu_arm is not None and n_verify:
+            bad = 0
+            picks = [int(np.flatnonzero(qb == bi)[0]) for bi in range(len(synth.DF_BUCKETS)) if np.any(qb == bi)]
+            for qi in picks:
+                _lib.check(L.sa_score_term(h, int(term_ids[qi]), float(idf[qi]), float(avgdl), K1, B, 0, _lib.ALL_BITS,
+                                           _lib.p_f32(out)))
+                want = cpu_arm.score_term(int(term_ids[qi]))
+                if not np.array_equal(out.view(np.uint32), want.view(np.uint32)):
+                    bad += 1
+            verify = verify or {}
+            verify["dense"] = {"vectors_checked": len(picks), "mismatches": bad,
+                               "what": "sa_score_term float32[N] bit-for-bit vs the CPU %s's .score(), one term per df bucket"
+                                       % cpu_arm.kind}
+            log("verify dense:", verify["dense"])
 
-    # ---- cpu_baseline (rank 0, N=1): oracle port on the host cores, bounded sample
+    # ---- cpu_baseline (rank 0, N=1): the reference's .score() on the host cores, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu_arm is not None:
         cores = os.cpu_count() or 1
-        idx, one = cpu_reference_runner(host, avgdl, args.docs, k)
-        for t in np.unique(term_ids):
-            idx.docfreq(int(t))
-            idx.termfreqs(int(t))
         sample = term_ids[:min(Q, args.ref_sample)]
-        threads = best_thread_count(one, sample, cores)
+        cpu_arm.warm(sample, threads=min(cores, 32))
+        threads, _ = best_thread_count(cpu_arm.score_term, sample, cores)
         tt, n = 0.0, 0
         while tt < 10.0 and n < 8:
-            tt += run_cpu_sample(one, sample, threads)
+            tt += run_cpu_sample(cpu_arm.score_term, sample, threads)
             n += 1
+        one_thread = len(sample[:32]) / run_cpu_sample(cpu_arm.score_term, sample[:32], 1)
+        tk = sample[:24]
+        topk_qps = len(tk) / run_cpu_sample(lambda q: cpu_topk(cpu_arm.score_term(q), k), tk, min(threads, 8))
         cpu = {"value": n * len(sample) / tt, "unit": "queries/s", "cores": threads, "host_cores": cores,
-               "kind": "port",
-               "sample": f"{n} x {len(sample)} of the step's queries, ThreadPool({threads}) = fastest of the "
-                         "probed pool widths, warm tf cache, score over all N + argpartition top-k"}
-        # parity spot-check of the GPU top-k against the oracle on the sample
-        bad = 0
-        for qi in range(min(16, len(sample))):
-            ref = one(int(sample[qi]))
-            s_ref = idx.score(int(sample[qi]), k1=K1, b=B)
-            order = np.lexsort((np.arange(len(s_ref)), -s_ref.astype(np.float64)))[:k]
-            if not np.array_equal(out_docs[qi], order.astype(np.uint32)):
-                bad += 1
-            del ref
-        cpu["gpu_topk_mismatches_in_16"] = bad
+               "kind": cpu_arm.kind,
+               "sample": f"{n} x {len(sample)} of the step's queries, stock SearchArray.score (dense float32[N], no top-k), "
+                         f"ThreadPool({threads}) = fastest of the probed pool widths, warm tf/df caches",
+               "one_thread": {"value": one_thread, "unit": "queries/s"},
+               "score_plus_topk": {"value": topk_qps, "unit": "queries/s",
+                                   "note": "score + flatnonzero/argpartition top-k, informational"}}
         try:
-            cpu["cold"] = cold_cpu_qps(idx, one, sample)
+            cpu["cold"] = cold_cpu_qps(cpu_arm, sample)
         except Exception as e:                      # informational; never fail the run for it
             cpu["cold"] = {"error": repr(e)}
-
-    verify = None
-    if rank == 0 and args.verify:
-        from oracle import ops as oops, search as osearch
-        from searcharray_b200 import synth
-        from searcharray_b200.shard import shard_topk_keys, unpack_keys
-        full, _, _ = (host, lo, hi) if world == 1 else synth.generate_shard(spec, 0, 1)
-        bad = 0
-        for qi in range(min(args.verify, Q)):
-            t = int(term_ids[qi])
-            ids, tfs = osearch.termfreqs_sparse(full.term_words(t))
-            sc = tfs.copy()
-            oops.bm25_score(sc, full.doc_lens[ids.astype(np.int64)], avgdl, float(idf[qi]), K1, B)
-            wd, ws = unpack_keys(shard_topk_keys(ids, sc, k))
-            if not (np.array_equal(wd, out_docs[qi]) and np.array_equal(ws.view(np.uint32), out_scores[qi].view(np.uint32))):
-                bad += 1
-        verify = {"queries_checked": min(args.verify, Q), "mismatches": bad}
-        log("verify:", verify)
 
     if rank == 0:
         line = {
@@ -671,12 +767,85 @@ def bench_ours(args, rank, world):
             "cpu_baseline": cpu,
             "e2e_dense": e2e_dense,
             "phrase": phrase,
+            "bigram": bigram,
             "edismax": edis,
             "topk_overflow_reruns": int(overflow),
             "verify": verify,
         }
         print(json.dumps(line), flush=True)
-    dev.close()
+    o.dev.close()
+
+
+def edismax_block(args, o, cpu_arm):
+    import pandas as pd
+    from searcharray_b200 import SearchArray, solr, synth
+    from searcharray_b200.shard import ShardComm
+    _lib, L = o._lib, o.L
+    k, rank, world = args.k, o.rank, o.world
+    t0 = time.time()
+    tspec, thost, _, _, t_avgdl = build_corpus(args.docs, rank, world, field="title")
+    comm = ShardComm(o.h, rank, world)
+    body = SearchArray.from_host_index(o.host, device=o.local_rank, doc_base=o.lo, corpus_size=args.docs,
+                                       avg_doc_length=o.avgdl, global_df=o.df, comm=comm)
+    body._shared["dev"] = o.dev                      # the body shard is already in HBM
+    title = SearchArray.from_host_index(thost, device=o.local_rank, doc_base=o.lo, corpus_size=args.docs,
+                                        avg_doc_length=t_avgdl, comm=comm)
+    tdev = title._device()
+    tdf = np.zeros(thost.n_terms, dtype=np.uint64)
+    tmp = ctypes.c_uint64(0)
+    for t in range(thost.n_terms):
+        _lib.check(L.sa_docfreq(tdev.handle, t, ctypes.byref(tmp)))
+        tdf[t] = tmp.value
+    title.global_df = comm.sum_u64(tdf)
+    frame = pd.DataFrame({"title": title, "body": body})
+    log(f"edismax: title field {thost.words.nbytes / 1e6:.0f} MB of postings, avgdl={t_avgdl}, "
+        f"set-up {time.time() - t0:.1f}s")
+    eq = synth.edismax_queries(o.spec, args.edismax_queries)
+    ekw = dict(qf=["title^1.0", "body^0.5"], pf=["title", "body"], pf2=["title", "body"], pf3=["title", "body"],
+               mm=2, tie=0.3)
+    for qtext in eq[:3]:
+        solr.edismax_topk(frame, qtext, k=k, **ekw)
+    o.barrier()
+    solr._TIMING = {}
+    t0 = time.perf_counter()
+    hits = 0
+    for qtext in eq:
+        d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
+        hits += int(d_[0] != 0xFFFFFFFF)
+    o.barrier()
+    e_s = o.max_over_ranks(time.perf_counter() - t0)
+    call_ms = {kk: 1e3 * vv / len(eq) for kk, vv in solr._TIMING.items()}
+    solr._TIMING = None
+    edis = {"workload": "two-field edismax (title^1.0 body^0.5, pf/pf2/pf3 on both fields as test_msmarco.py:436-443, mm=2, "
+                        "tie=0.3), mixed 2-5 term queries, exact float64 top-%d" % k,
+            "queries": len(eq), "e2e": {"value": len(eq) / e_s, "unit": "queries/s"},
+            "ms_per_query": 1e3 * e_s / len(eq), "queries_with_hits": hits,
+            "ms_per_query_by_call": call_ms}
+    if cpu_arm is not None:
+        from oracle import search as osearch, solr as osolr
+        ofields = {}
+        for name, hidx, adl in (("title", thost, t_avgdl), ("body", o.host, o.avgdl)):
+            oi = osearch.OracleIndex({t: hidx.term_words(t) for t in range(hidx.n_terms)}, hidx.doc_lens,
+                                     avg_doc_length=adl, corpus_size=args.docs, cache=True)
+            ofields[name] = osolr.OracleField(oi, hidx.term_dict.term_to_ids)
+        nq = min(args.verify_edismax, len(eq))
+        t_cpu, bad = 0.0, 0
+        for qtext in eq[:nq]:
+            t0 = time.perf_counter()
+            want = osolr.edismax(ofields, qtext, **ekw)
+            t_cpu += time.perf_counter() - t0
+            d_, s_ = solr.edismax_topk(frame, qtext, k=k, **ekw)
+            order = np.lexsort((np.arange(len(want)), -want))[:k]
+            order = order[want[order] > 0]
+            if not (np.array_equal(d_[:len(order)], order.astype(np.uint32)) and
+                    np.allclose(s_[:len(order)], want[order], rtol=1e-5, atol=0)):
+                bad += 1
+        edis["cpu_baseline"] = {"kind": "port", "cores": 1, "value": nq / t_cpu, "unit": "queries/s",
+                                "sample": f"{nq} of the queries, oracle port of solr.py (oracle/solr.py)"}
+        edis["verify"] = {"queries_checked": nq, "mismatches": bad,
+                          "what": "top-%d docs exact, float64 scores within 1e-5 vs oracle/solr.py" % k}
+    del frame, title, tdev
+    return edis
 
 
 def main():
@@ -689,13 +858,18 @@ def main():
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--ref-sample", type=int, default=192)
+    ap.add_argument("--ref-budget", type=float, default=150.0,
+                    help="reference arm: target seconds for all --steps + --warmup passes (bounds the per-step sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phrase-queries", type=int, default=256)
-    ap.add_argument("--slop-queries", type=int, default=16)
+    ap.add_argument("--slop-queries", type=int, default=256)
+    ap.add_argument("--bigram-queries", type=int, default=32)
     ap.add_argument("--edismax-queries", type=int, default=48)
-    ap.add_argument("--verify", type=int, default=0,
-                    help="rank 0 re-generates the FULL corpus and checks this many queries' global top-k "
-                         "against the CPU oracle (parity of the sharded / all-gathered path)")
+    ap.add_argument("--verify", type=int, default=-1,
+                    help="term queries whose global top-k (docs + score bits) is checked against the CPU oracle "
+                         "(default 48 at 1 GPU, 16 sharded -- rank 0 then re-generates the FULL corpus; 0 = off)")
+    ap.add_argument("--verify-phrases", type=int, default=12)
+    ap.add_argument("--verify-edismax", type=int, default=2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -143,6 +143,11 @@ typedef struct {
     double phrase_kernel_ms;
     uint64_t phrase_kernel_launches;
     uint64_t total_launches;          /* every kernel launched by the library */
+    /* phrase (slop 0) batches, summed over the queries of every sa_batch_download since the reset:
+     * continuation words written (sum of C_s) and docs with a non-zero phrase count (M) -- the
+     * data-dependent terms of SURVEY 8d's B_phrase = 8*sum(W) + 16*sum(C_s) + 4*N + 4*M */
+    uint64_t phrase_cont_words;
+    uint64_t phrase_matched_docs;
 } sa_stats;
 int sa_stats_reset(sa_index *index);
 int sa_stats_get(sa_index *index, sa_stats *out);

@@ -24,7 +24,8 @@ class SaStats(ctypes.Structure):
     _fields_ = [("term_kernel_ms", ctypes.c_double), ("term_kernel_launches", c_u64),
                 ("term_kernel_queries", c_u64), ("topk_kernel_ms", ctypes.c_double),
                 ("topk_kernel_launches", c_u64), ("phrase_kernel_ms", ctypes.c_double),
-                ("phrase_kernel_launches", c_u64), ("total_launches", c_u64)]
+                ("phrase_kernel_launches", c_u64), ("total_launches", c_u64),
+                ("phrase_cont_words", c_u64), ("phrase_matched_docs", c_u64)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/searcharray_b200.h declares
@@ -121,23 +122,3 @@ def p_u32(a):
 
 def p_f32(a):
     return a.ctypes.data_as(P_f32)
-
-
-class PinnedPool:
-    """float32 result vectors in pinned host memory (cudaHostAlloc) so the dense
-    float32[N] D2H copy runs at PCIe rate instead of through a pageable bounce."""
-
-    def __init__(self):
-        self._live = {}
-
-    def empty_f32(self, n):
-        ptr = P_void()
-        check(lib().sa_host_alloc(ctypes.byref(ptr), max(int(n), 1) * 4))
-        buf = (c_f32 * max(int(n), 1)).from_address(ptr.value)
-        arr = np.frombuffer(buf, dtype=np.float32, count=int(n))
-        return arr, ptr
-
-    @staticmethod
-    def free(ptr):
-        if _lib is not None:
-            _lib.sa_host_free(ptr)

@@ -18,7 +18,20 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+SYNTH_LIB = os.path.join(HERE, "libsa_synth.so")
+
+
+def build_synth(force=False):
+    """The synthetic-corpus generator (host C + pthreads; bench / test data infrastructure)."""
+    src = os.path.join(CSRC, "sa_synth.c")
+    if force or _newer(SYNTH_LIB, [src]):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-pthread", "-shared", "-fPIC", "-Wall",
+                               "-o", SYNTH_LIB, src, "-lm"])
+    return SYNTH_LIB
+
+
 def build(force=False, verbose=False):
+    build_synth(force)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "searcharray_b200.h"))

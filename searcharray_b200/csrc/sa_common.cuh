@@ -52,12 +52,12 @@ struct DevBuf {
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return SA_OK;
+        // grow geometrically: cudaFree + cudaMalloc synchronise the device, so a buffer that creeps up
+        // query by query must not be reallocated on every new maximum
+        const size_t want = std::max(bytes + (bytes >> 3), cap + (cap >> 1)) + 256;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        // grow geometrically: cudaFree + cudaMalloc synchronise the device, so a buffer that creeps up
-        // query by query must not be reallocated on every new maximum
-        size_t want = std::max(bytes + (bytes >> 3), cap + (cap >> 1)) + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             sa_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));

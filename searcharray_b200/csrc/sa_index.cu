@@ -726,6 +726,10 @@ int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
     std::vector<u32> ovf((const u32 *)ix->h_pinned, (const u32 *)ix->h_pinned + B.nq);       // row space
     std::vector<PhraseStats> st(B.pqs.size());
     if (st_bytes) memcpy(st.data(), (char *)ix->h_pinned + ovf_bytes, st_bytes);
+    for (const PhraseStats &s : st) {
+        ix->stats.phrase_cont_words += s.n_cont;
+        ix->stats.phrase_matched_docs += s.n_match;
+    }
     struct Redo { bool phrase; u32 idx, q; const SpanQuery *sq; };
     std::vector<Redo> redo;
     size_t chunk_i = 0;

@@ -411,6 +411,7 @@ phrase_kernel(const PhraseArgs a) {
             if (tid == 0) {
                 if (S.st_inner) atomicAdd(&a.stats[q].n_inner[tnew], S.st_inner);
                 if (S.st_diff) atomicAdd(&a.stats[q].n_diff[tnew], S.st_diff);
+                if (n_cont) atomicAdd(&a.stats[q].n_cont, (unsigned long long)n_cont);
             }
             __syncthreads();
             if (prev_docs) and_min(docs_out, n_docs, prev_docs, n_prev);
@@ -499,17 +500,20 @@ phrase_kernel(const PhraseArgs a) {
         for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
             reinterpret_cast<float4 *>(s_tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        u32 my_max = 0;
+        u32 my_max = 0, my_match = 0;
         for (u64 i = m0 + tid; i < m1; i += PT) {
             const u64 e = fin.docs[i];
             const u32 c = (u32)(e & 0xFFFFFFFFull);
             if (c == 0) continue;
             const u64 d = (e >> 32) - a.doc_base;
             if (d >= a.n_docs) continue;
+            my_match++;
             const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
             s_tile[d - (u64)tile * SA_TILE_DOCS] = v;
             if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
         }
+        my_match = __reduce_add_sync(0xffffffffu, my_match);
+        if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
         __syncthreads();
         flush_tile_collect(s_tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
                            s_top, &s_ncand, &s_tile_max);

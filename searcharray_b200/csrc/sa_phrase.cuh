@@ -24,7 +24,8 @@ struct PhraseStats {      // per query, accumulated over all chunks (global atom
     u32 n_inner[SA_MAX_PHRASE_TERMS];   // equal-header pairs seen at step s
     u32 n_diff[SA_MAX_PHRASE_TERMS];    // ... of which lhs word != rhs word
     u32 overflow;                        // scratch arena exhausted
-    u32 pad;
+    u32 n_match;                         // docs with a non-zero phrase count (M of SURVEY 8d's B_phrase)
+    unsigned long long n_cont;           // continuation words written over all steps (sum of C_s)
 };
 
 // Optional dump of one CTA's final lists (per-op parity export; needs n_chunks == 1).

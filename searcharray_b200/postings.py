@@ -97,18 +97,32 @@ class TermsDtype(ExtensionDtype):
 
 class _PinnedPool:
     """Result vectors live in pinned host memory so the float32[N] D2H copy runs at PCIe
-    rate; buffers are recycled when the numpy array that views them is garbage-collected."""
+    rate; buffers are recycled when the numpy array that views them is garbage-collected.
+    Sizes are bucketed to powers of two (so differently sized slices share buffers) and the idle
+    pool is capped: beyond the cap a released buffer goes back to the driver (sa_host_free)."""
+
+    MAX_IDLE_BYTES = 1 << 30
 
     def __init__(self):
         self._free = {}
+        self._idle = 0
         self._lock = threading.Lock()
+
+    @staticmethod
+    def _bucket(nbytes):
+        b = 4096
+        while b < nbytes:
+            b <<= 1
+        return b
 
     def empty_f32(self, n):
         n = int(n)
-        nbytes = max(n, 1) * 4
+        nbytes = self._bucket(max(n, 1) * 4)
         with self._lock:
             lst = self._free.get(nbytes)
             ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self._idle -= nbytes
         if ptr is None:
             p = ctypes.c_void_p()
             _lib.check(_lib.lib().sa_host_alloc(ctypes.byref(p), nbytes))
@@ -119,7 +133,12 @@ class _PinnedPool:
 
     def _release(self, nbytes, ptr):
         with self._lock:
-            self._free.setdefault(nbytes, []).append(ptr)
+            if self._idle + nbytes <= self.MAX_IDLE_BYTES:
+                self._free.setdefault(nbytes, []).append(ptr)
+                self._idle += nbytes
+                return
+        if _lib._lib is not None:
+            _lib._lib.sa_host_free(ctypes.c_void_p(ptr))
 
 
 _pool = _PinnedPool()
@@ -188,7 +207,7 @@ class SearchArray(ExtensionArray):
         self.doc_base = 0
         self.global_df = None            # uint64[n_terms] document frequencies over all shards
         self.comm = None                 # shard.ShardComm: sums over ranks where a query needs them
-        self._shared = {"dev": None, "lock": threading.Lock()}   # shared by views/copies
+        self._shared = {"dev": None, "lock": threading.RLock()}   # shared by views/copies
 
     @classmethod
     def index(cls, array, tokenizer=ws_tokenizer, truncate=False, batch_size=100000, avoid_copies=True,
@@ -237,7 +256,7 @@ class SearchArray(ExtensionArray):
 
     def __setstate__(self, st):
         self.__dict__.update(st)
-        self._shared = {"dev": None, "lock": threading.Lock()}
+        self._shared = {"dev": None, "lock": threading.RLock()}
 
     # ------------------------------------------------------------ ExtensionArray bits
     @classmethod
@@ -259,8 +278,8 @@ class SearchArray(ExtensionArray):
 
     def _row_terms(self, doc_id):
         post = {}
-        key = np.uint64(doc_id) << np.uint64(36)
-        nxt = np.uint64(doc_id + 1) << np.uint64(36)
+        key = np.uint64(doc_id + self.doc_base) << np.uint64(36)     # words carry ABSOLUTE doc ids (shards)
+        nxt = np.uint64(doc_id + self.doc_base + 1) << np.uint64(36)
         for t in range(self.host.n_terms):
             w = self.host.term_words(t)
             a, b = np.searchsorted(w, key), np.searchsorted(w, nxt)
@@ -449,6 +468,7 @@ class SearchArray(ExtensionArray):
         w = self.host.term_words(tid)
         out = []
         for d in np.atleast_1d(docs):
+            d = int(d) + self.doc_base                       # words carry ABSOLUTE doc ids (shards)
             a = np.searchsorted(w, np.uint64(d) << np.uint64(36))
             b = np.searchsorted(w, np.uint64(d + 1) << np.uint64(36))
             out.append(decode_positions(w[a:b]))
@@ -457,7 +477,11 @@ class SearchArray(ExtensionArray):
     # -------------------------------------------------- batched, HBM-resident path
     def search_topk(self, queries, k=10, similarity: Bm25Similarity = default_bm25, slop=0):
         """queries: list of str (term) or list[str] (phrase).  Returns (docs uint32[Q,k],
-        scores float32[Q,k]); scores never leave HBM except the top-k (sa_score_batch_topk)."""
+        scores float32[Q,k]); scores never leave HBM except the top-k (sa_score_batch_topk).
+        Defined on unsliced arrays only: a sliced view scores through .score() (FilteredPosns semantics)."""
+        if self.rows is not None:
+            raise ValueError("search_topk on a sliced SearchArray is not supported: the batched path scores the "
+                             "whole shard; use .score() on the slice")
         terms, starts, idfs = [], [0], []
         for q in queries:
             toks = [q] if isinstance(q, str) else list(q)

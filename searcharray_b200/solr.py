@@ -126,12 +126,33 @@ _multis_lock = threading.Lock()
 def _multi_for(arrays: List[SearchArray]) -> _Multi:
     key = tuple(id(a._device()) for a in arrays)
     with _multis_lock:
-        m = _multis.get(key)
+        m = _multis.pop(key, None)
         if m is None:
-            if len(_multis) > 16:
-                _multis.clear()
-            m = _multis[key] = _Multi(arrays)
+            while len(_multis) >= 16:                 # evict the least recently used; a caller still
+                _multis.pop(next(iter(_multis)))      # holding it keeps it alive until it is done
+            m = _Multi(arrays)
+        _multis[key] = m                              # most recently used last
         return m
+
+
+class _locked:
+    """Holds the multi's lock AND every participating array's device lock (in a fixed order) for a whole
+    edismax evaluation: the sa_multi_* calls keep intermediate state in the field indexes' scratch
+    buffers, which a concurrent .score()/.termfreqs() on the same array would overwrite."""
+
+    def __init__(self, multi: _Multi, arrays: List[SearchArray]):
+        uniq = {id(a._shared["lock"]): a._shared["lock"] for a in arrays}
+        self.locks = [multi.lock] + [uniq[k] for k in sorted(uniq)]
+
+    def __enter__(self):
+        for lk in self.locks:
+            lk.acquire()
+        return self
+
+    def __exit__(self, *exc):
+        for lk in reversed(self.locks):
+            lk.release()
+        return False
 
 
 def _u32(values):
@@ -208,10 +229,11 @@ class _Plan:
         return text
 
 
-def _run_device(plan: _Plan) -> _Multi:
-    """qf phase + phrase phases into the multi's HBM-resident combined vector."""
+def _run_device(plan: _Plan, multi: _Multi) -> _Multi:
+    """qf phase + phrase phases into the multi's HBM-resident combined vector (caller holds `_locked`)."""
     L = _lib.lib()
-    multi = _multi_for(plan.arrays)
+    for arr in plan.arrays:                    # a sliced view of the same column may have left its row filter installed
+        arr._apply_rows(arr._device())
     F = len(plan.names)
     n_terms, tids, idfs, boosts, has_boost, avgdl, k1, b, mms = [], [], [], [], [], [], [], [], []
     for f, arr in zip(plan.names, plan.arrays):
@@ -354,8 +376,9 @@ def edismax(frame: pd.DataFrame, q: str, qf: List[str], mm: Optional[Union[str, 
     if not plan.device_ok():
         return _run_composed(plan), explain
     n = len(plan.arrays[0])
-    with _multi_for(plan.arrays).lock:
-        multi = _run_device(plan)
+    multi = _multi_for(plan.arrays)
+    with _locked(multi, plan.arrays):
+        _run_device(plan, multi)
         out = np.empty(n, dtype=np.float64 if plan.term_centric else np.float32)
         _lib.check(_lib.lib().sa_multi_download(multi.handle, out.ctypes.data_as(ctypes.c_void_p),
                                                 0 if plan.term_centric else 1))
@@ -373,8 +396,9 @@ def edismax_topk(frame: pd.DataFrame, q: str, qf: List[str], k: int = 10, mm: Op
         raise NotImplementedError("edismax_topk needs BM25 similarities on unsliced SearchArray columns")
     docs = np.empty(k, dtype=np.uint32)
     scores = np.empty(k, dtype=np.float64)
-    with _multi_for(plan.arrays).lock:
-        multi = _run_device(plan)
+    multi = _multi_for(plan.arrays)
+    with _locked(multi, plan.arrays):
+        _run_device(plan, multi)
         _lib.check(_timed("topk", _lib.lib().sa_multi_topk, multi.handle, k, _lib.p_u32(docs),
                                             scores.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
     comm = plan.arrays[0].comm

@@ -20,8 +20,8 @@ def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     n_docs, k = 160_000, 10
-    spec = synth.SynthSpec(n_docs, terms_per_bucket=2, n_phrase_groups=0)
-    host, lo, hi = synth.generate_shard(spec, rank, world)
+    spec = synth.SynthSpec(n_docs, terms_per_bucket=2, n_phrases=0, n_bigrams=0)
+    host, lo, hi = synth.generate_shard(spec, rank, world, n_threads=2)
     assert len(host.doc_lens) == hi - lo
     # global statistics: df by all-reduce, avgdl from the generator's blocks
     df_local = np.asarray([osearch.docfreq(host.term_words(t)) for t in range(host.n_terms)], dtype=np.int64)
@@ -29,8 +29,7 @@ def main():
     df_t = torch.from_numpy(df_local.copy())
     dist.all_reduce(df_t)
     df = df_t.numpy()
-    total = sum(float(np.sum(synth.gen_doc_lens(n_docs, b), dtype=np.float64)) for b in range(synth.N_BLOCKS))
-    avgdl = np.float32(total / n_docs)
+    avgdl = synth.global_avg_doc_length(spec)
 
     results = []
     for t in range(host.n_terms):

@@ -22,7 +22,7 @@ def test_two_rank_gloo_sharded_topk():
 
 def test_shards_tile_the_corpus():
     from searcharray_b200 import synth
-    spec = synth.SynthSpec(40_000, terms_per_bucket=1, n_phrase_groups=2)
+    spec = synth.SynthSpec(40_000, terms_per_bucket=2, n_phrases=8, n_bigrams=2)
     full, lo, hi = synth.generate_shard(spec, 0, 1)
     assert (lo, hi) == (0, 40_000)
     for world in (2, 4, 8):
@@ -31,6 +31,45 @@ def test_shards_tile_the_corpus():
         assert np.array_equal(np.concatenate([p[0].doc_lens for p in parts]), full.doc_lens)
         for t in range(full.n_terms):
             assert np.array_equal(np.concatenate([p[0].term_words(t) for p in parts]), full.term_words(t))
+    # deterministic whatever the number of generator threads; global avgdl = mean of the whole corpus
+    one, _, _ = synth.generate_shard(spec, 0, 1, n_threads=1)
+    assert np.array_equal(one.words, full.words) and np.array_equal(one.doc_lens, full.doc_lens)
+    assert synth.global_avg_doc_length(spec) == np.float32(np.sum(full.doc_lens, dtype=np.float64) / 40_000)
+
+
+def test_synth_corpus_is_well_formed():
+    """Every term's list is sorted and header-unique (the index's upload format), df follows the
+    bucket, planted phrases really occur, and the query sets are distinct."""
+    from oracle import search as osearch
+    from searcharray_b200 import synth
+    n = 200_000
+    spec = synth.SynthSpec(n, terms_per_bucket=6, n_phrases=16, n_bigrams=4)
+    host, _, _ = synth.generate_shard(spec)
+    for t, (name, p, _) in enumerate(spec.terms):
+        w = host.term_words(t)
+        assert np.all(np.diff((w >> np.uint64(18)).astype(np.int64)) > 0)
+        assert np.all((w & np.uint64(0x3FFFF)) != 0)
+        docs = (w >> np.uint64(36)).astype(np.int64)
+        assert docs.min() >= 0 and docs.max() < n
+        posn_ok = ((w >> np.uint64(18)) & np.uint64(0x3FFFF)).astype(np.int64) * 18 < host.doc_lens[docs]
+        assert posn_ok.all()
+        df = len(np.unique(docs))
+        assert abs(df - p * n) < 6 * np.sqrt(p * n) + 0.2 * p * n + 30, (name, df, p * n)
+    oidx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens)
+    for ph in spec.phrases:
+        ids = [spec.term_index[t] for t in ph["terms"]]
+        exact = np.count_nonzero(oidx.termfreqs(ids))
+        sloppy = np.count_nonzero(oidx.termfreqs(ids, slop=2))
+        assert sloppy >= exact
+        if ph["plant_p"] * n >= 20:
+            assert exact >= 1, ph
+            if ph["gapped"]:
+                assert sloppy > exact, ph
+    q = synth.stratified_term_queries(spec, len(spec.terms))
+    assert len(set(q)) == len(spec.terms)
+    pq = synth.phrase_queries(spec, 16)
+    assert len({tuple(x) for x in pq}) == 16 and set(synth.phrase_kinds(spec, pq)) == {"rare", "hard"}
+    assert all(len(x) == 2 for x in synth.bigram_queries(spec, 4))
 
 
 def test_key_roundtrip_and_merge():

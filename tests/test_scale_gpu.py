@@ -1,0 +1,130 @@
+"""GPU parity at the BASELINE configs' scale: the seeded synthetic corpus of bench.py
+(searcharray_b200/synth.py) at 2M docs with the full 1,024-term vocabulary, and at 10M docs (the size
+BASELINE configs[1]-[3] are quoted on) with a reduced vocabulary, against the CPU oracle:
+  * dense `score` vectors bit for bit for terms of every df bucket,
+  * phrase (slop 0) and slop-2 dense counts for phrases of every kind (rare / hard / bigram),
+  * the batched top-k: doc ids AND score bits.
+Tile directories, multi-chunk phrase CTAs, (queries, tiles) grids and dense-row chunking only engage at
+this scale."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+K1, B = 1.2, 0.75
+
+
+def build(n_docs, **kw):
+    from oracle import search as osearch
+    from searcharray_b200 import SearchArray, synth
+    spec = synth.SynthSpec(n_docs, **kw)
+    host, _, _ = synth.generate_shard(spec)
+    avgdl = synth.global_avg_doc_length(spec)
+    host.avg_doc_length = avgdl
+    arr = SearchArray.from_host_index(host, avg_doc_length=avgdl)
+    oidx = osearch.OracleIndex({t: host.term_words(t) for t in range(host.n_terms)}, host.doc_lens,
+                               avg_doc_length=avgdl, corpus_size=host.n_docs, cache=False)
+    return spec, host, arr, oidx
+
+
+def bits_equal(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def oracle_topk(dense, k):
+    nz = np.flatnonzero(dense > 0)
+    order = nz[np.lexsort((nz, -dense[nz].astype(np.float64)))][:k]
+    docs = np.full(k, 0xFFFFFFFF, dtype=np.uint32)
+    scores = np.zeros(k, dtype=np.float32)
+    docs[:len(order)] = order
+    scores[:len(order)] = dense[order]
+    return docs, scores
+
+
+def check_corpus(spec, host, arr, oidx, terms_per_bucket, n_rare, n_hard, n_bigram, n_slop):
+    from searcharray_b200 import synth
+    k = 10
+    # ---- terms: dense tf + score vectors, one or more per df bucket, and the batched top-k of all of them
+    names = []
+    for bi in range(len(synth.DF_BUCKETS)):
+        names.extend(spec.bucket_terms[bi][:terms_per_bucket])
+    want_scores = {}
+    for nm in names:
+        t = spec.term_index[nm]
+        assert int(arr.docfreq(nm)) == int(oidx.docfreq(t)), nm
+        assert bits_equal(arr.termfreqs(nm), oidx.termfreqs(t)), nm
+        want_scores[nm] = oidx.score(t, k1=K1, b=B)
+        assert bits_equal(arr.score(nm), want_scores[nm]), nm
+    docs, scores = arr.search_topk(names, k=k)
+    for i, nm in enumerate(names):
+        wd, ws = oracle_topk(want_scores[nm], k)
+        assert np.array_equal(docs[i], wd), nm
+        assert bits_equal(scores[i], ws), nm
+    # ---- phrases of every kind: dense counts, dense scores, batched top-k
+    rare = [ph for ph in spec.phrases if ph["kind"] == "rare"][:n_rare]
+    hard = [ph for ph in spec.phrases if ph["kind"] == "hard"][:n_hard]
+    big = [ph for ph in spec.phrases if ph["kind"] == "bigram"][:n_bigram]
+    phrases = [ph["terms"] for ph in rare + hard + big]
+    want = {}
+    n_match = 0
+    for ph in phrases:
+        ids = [spec.term_index[t] for t in ph]
+        tf = oidx.termfreqs(ids)
+        assert bits_equal(arr.termfreqs(ph), tf), ph
+        want[tuple(ph)] = oidx.score(ids, k1=K1, b=B)
+        assert bits_equal(arr.score(ph), want[tuple(ph)]), ph
+        n_match += int(np.count_nonzero(tf))
+    assert n_match > 0
+    for group in (phrases[:len(rare) + len(hard)], phrases[len(rare) + len(hard):]):
+        if not group:
+            continue
+        docs, scores = arr.search_topk(group, k=k)
+        for i, ph in enumerate(group):
+            wd, ws = oracle_topk(want[tuple(ph)], k)
+            assert np.array_equal(docs[i], wd), ph
+            assert bits_equal(scores[i], ws), ph
+    # ---- slop 2
+    from oracle import ops as oops
+    sl = [ph["terms"] for ph in (rare[:n_slop] + hard[:max(1, n_slop // 2)])]
+    ok = []
+    for ph in sl:
+        ids = [spec.term_index[t] for t in ph]
+        tf = oidx.termfreqs(ids, slop=2)
+        if oops.last_span_undefined:          # the reference's 512-slot table overflowed: undefined, excluded
+            continue
+        assert bits_equal(arr.termfreqs(ph, slop=2), tf), ph
+        want[("slop",) + tuple(ph)] = oidx.score(ids, k1=K1, b=B, slop=2)
+        ok.append(ph)
+    assert ok
+    docs, scores = arr.search_topk(ok, k=k, slop=2)
+    for i, ph in enumerate(ok):
+        wd, ws = oracle_topk(want[("slop",) + tuple(ph)], k)
+        assert np.array_equal(docs[i], wd), ph
+        assert bits_equal(scores[i], ws), ph
+
+
+def test_2m_docs_full_vocabulary():
+    spec, host, arr, oidx = build(2_000_000)
+    assert host.n_terms == 1024
+    check_corpus(spec, host, arr, oidx, terms_per_bucket=3, n_rare=12, n_hard=6, n_bigram=4, n_slop=4)
+    # every one of the 1,024 distinct terms through the batched path: top-1 doc and score bits vs sparse oracle
+    from oracle import ops as oops, search as osearch
+    names = [t[0] for t in spec.terms]
+    docs, scores = arr.search_topk(names, k=10)
+    from searcharray_b200.shard import shard_topk_keys, unpack_keys
+    from searcharray_b200.similarity import compute_idf
+    for i in range(0, len(names), 7):
+        ids, tfs = osearch.termfreqs_sparse(host.term_words(i))
+        idf = compute_idf(host.n_docs, np.asarray([len(ids)]))
+        sc = tfs.copy()
+        oops.bm25_score(sc, host.doc_lens[ids.astype(np.int64)], host.avg_doc_length, np.float32(idf), K1, B)
+        wd, ws = unpack_keys(shard_topk_keys(ids, sc, 10))
+        assert np.array_equal(docs[i], wd), names[i]
+        assert bits_equal(scores[i], ws), names[i]
+
+
+def test_10m_docs_baseline_size():
+    """BASELINE configs[1]-[3] at their stated size (10M docs), reduced vocabulary to bound the test time."""
+    spec, host, arr, oidx = build(10_000_000, terms_per_bucket=2, n_phrases=8, n_bigrams=2)
+    check_corpus(spec, host, arr, oidx, terms_per_bucket=1, n_rare=3, n_hard=2, n_bigram=1, n_slop=2)
