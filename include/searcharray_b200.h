@@ -241,6 +241,46 @@ int sa_op_bigram_freqs(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs,
                        uint64_t *ids_out, float *counts_out, uint64_t *n_ids_out,
                        uint64_t *next_out, uint64_t *n_next_out);
 
+/* The reference's sorted-set ops on raw arrays (sa_setops.cu), one export per Cython op, returning what the
+ * op returns (index arrays, not values, for the intersect family).  Inputs sorted by (x & mask) as every
+ * reference caller passes them; output capacities: intersect family min(n_lhs, n_rhs) per array (keep mode:
+ * n_lhs / n_rhs), merge n_lhs + n_rhs, the grouped ops and unique / payload_slice n.
+ *   sa_op_intersect                searcharray/roaringish/intersect.pyx:278-320 (drop_duplicates as there;
+ *                                  mask == 0 -> SA_ERR_ARG, the reference raises ValueError)
+ *   sa_op_adjacent                 :323-343   pairs with (lhs & mask) + lowbit(mask) == (rhs & mask)
+ *   sa_op_intersect_with_adjacents :346-390   both in one call
+ *   sa_op_merge                    searcharray/roaringish/merge.pyx:137-158
+ *   sa_op_sort_merge_counts        merge.pyx:211-232
+ *   sa_op_unique                   searcharray/roaringish/unique.pyx:139-145
+ *   sa_op_popcount64 / sa_op_popcount_reduce_at / sa_op_key_sum_over   popcount.pyx:120-122, 150-165, 195-204
+ *   sa_op_payload_slice / sa_op_as_dense   roaringish_ops.pyx:46-68, 84-98
+ * sa_op_last_staged_ctas: how many CTAs of the calling thread's last intersect-family call took the
+ * TMA-staged shared-memory path (the rest searched global memory): a test hook. */
+int sa_op_intersect(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                    uint64_t mask, int drop_duplicates, int device,
+                    uint64_t *lhs_idx_out, uint64_t *rhs_idx_out, uint64_t *n_lhs_out, uint64_t *n_rhs_out);
+int sa_op_adjacent(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                   uint64_t mask, int device, uint64_t *lhs_idx_out, uint64_t *rhs_idx_out, uint64_t *n_out);
+int sa_op_intersect_with_adjacents(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                                   uint64_t mask, int device,
+                                   uint64_t *lhs_idx_out, uint64_t *rhs_idx_out, uint64_t *n_out,
+                                   uint64_t *adj_lhs_idx_out, uint64_t *adj_rhs_idx_out, uint64_t *n_adj_out);
+int sa_op_merge(const uint64_t *lhs, uint64_t n_lhs, const uint64_t *rhs, uint64_t n_rhs,
+                int drop_duplicates, int device, uint64_t *out, uint64_t *n_out);
+int sa_op_sort_merge_counts(const uint64_t *lhs_ids, const float *lhs_counts, uint64_t n_lhs,
+                            const uint64_t *rhs_ids, const float *rhs_counts, uint64_t n_rhs,
+                            int device, uint64_t *ids_out, float *counts_out, uint64_t *n_out);
+int sa_op_unique(const uint64_t *arr, uint64_t n, uint64_t rshift, int device, uint64_t *out, uint64_t *n_out);
+int sa_op_popcount64(const uint64_t *arr, uint64_t n, int device, uint64_t *out);
+int sa_op_popcount_reduce_at(const uint64_t *ids, const uint64_t *payload, uint64_t n, int device,
+                             uint64_t *ids_out, float *counts_out, uint64_t *n_out);
+int sa_op_key_sum_over(const uint64_t *ids, const uint64_t *counts, uint64_t n, int device,
+                       uint64_t *ids_out, float *counts_out, uint64_t *n_out);
+int sa_op_payload_slice(const uint64_t *arr, uint64_t n, uint64_t msb_mask, uint64_t min_payload,
+                        uint64_t max_payload, int device, uint64_t *out, uint64_t *n_out);
+int sa_op_as_dense(const uint64_t *indices, const float *values, uint64_t n, uint64_t size, int device, float *out);
+uint64_t sa_op_last_staged_ctas(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,19 @@ SIGNATURES = {
     "sa_op_similarity": (c_int, [c_int, P_f32, P_f32, c_u64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                  ctypes.c_double, c_int, P_void]),
     "sa_op_bigram_freqs": (c_int, [P_u64, c_u64, P_u64, c_u64, c_int, c_int, P_u64, P_f32, P_u64, P_u64, P_u64]),
+    "sa_op_intersect": (c_int, [P_u64, c_u64, P_u64, c_u64, c_u64, c_int, c_int, P_u64, P_u64, P_u64, P_u64]),
+    "sa_op_adjacent": (c_int, [P_u64, c_u64, P_u64, c_u64, c_u64, c_int, P_u64, P_u64, P_u64]),
+    "sa_op_intersect_with_adjacents": (c_int, [P_u64, c_u64, P_u64, c_u64, c_u64, c_int, P_u64, P_u64, P_u64,
+                                               P_u64, P_u64, P_u64]),
+    "sa_op_merge": (c_int, [P_u64, c_u64, P_u64, c_u64, c_int, c_int, P_u64, P_u64]),
+    "sa_op_sort_merge_counts": (c_int, [P_u64, P_f32, c_u64, P_u64, P_f32, c_u64, c_int, P_u64, P_f32, P_u64]),
+    "sa_op_unique": (c_int, [P_u64, c_u64, c_u64, c_int, P_u64, P_u64]),
+    "sa_op_popcount64": (c_int, [P_u64, c_u64, c_int, P_u64]),
+    "sa_op_popcount_reduce_at": (c_int, [P_u64, P_u64, c_u64, c_int, P_u64, P_f32, P_u64]),
+    "sa_op_key_sum_over": (c_int, [P_u64, P_u64, c_u64, c_int, P_u64, P_f32, P_u64]),
+    "sa_op_payload_slice": (c_int, [P_u64, c_u64, c_u64, c_u64, c_u64, c_int, P_u64, P_u64]),
+    "sa_op_as_dense": (c_int, [P_u64, P_f32, c_u64, c_u64, c_int, P_f32]),
+    "sa_op_last_staged_ctas": (c_u64, []),
 }
 
 _lib = None

@@ -90,10 +90,16 @@ struct Bm25Params {
 struct TermQuery {
     u64 word_off;      // offset of the term's first word in d_words
     u64 n_words;       // 0 => unknown term (zeros)
-    u64 dir_off;       // offset of the term's tile directory in d_tile_dir, or SA_NO_DIR
+    u64 dir_off;       // offset of the term's tile directory in d_tile_dir (and d_rec_dir), or SA_NO_DIR
+    u64 rec_off;       // offset of the term's (doc, tf) records in d_recs, or SA_NO_DIR
     float idf;
     u32 pad;
 };
+
+// (doc, tf) record of the per-term tf table: doc index RELATIVE to its 8192-doc tile in the high 13 bits,
+// term frequency (sum of the doc's payload popcounts, < 2^18 + 1) in the low 19
+#define SA_REC_TF_BITS 19
+#define SA_REC_TF_MASK 0x7FFFFu
 
 // ---- the index handle ---------------------------------------------------------------
 struct TimedLaunch;
@@ -114,6 +120,12 @@ struct sa_index {
     // doc lies in tile >= j, j = 0..n_tiles  (tile = 4096 docs).  Built on the device at upload.
     u32 *d_tile_dir = nullptr;
     std::vector<u64> h_dir_off;
+    // per-term tf table (the analogue of the reference's termfreq_cache, middle_out.py:501-509, built on the
+    // device at upload): for every term WITH a tile directory, one u32 record per (term, doc) in doc order,
+    // (doc - tile_doc0) << 19 | tf; d_rec_dir mirrors d_tile_dir (same offsets) with indices into the records.
+    u32 *d_recs = nullptr;
+    u32 *d_rec_dir = nullptr;
+    std::vector<u64> h_rec_off;
     // per-doc BM25 length norm k1*((1-b)+b*dl/avgdl) for the last used (k1, b, avgdl)
     float *d_norm = nullptr;         // [padded n_docs]
     float norm_k1 = 0, norm_b = 0, norm_avgdl = 0;

@@ -98,6 +98,130 @@ __global__ void tile_dir_kernel(const u64 *__restrict__ words, u64 n_words,
         for (u32 t = t_i + 1; t <= n_tiles; t++) d[t] = (u32)len;
 }
 
+// ---- tf table (see sa_index::d_recs).  Pass 1 counts the doc heads of every 1024-word block, a one-CTA scan
+// turns the counts into ranks, pass 2 writes each head's record at (term's record offset + rank within the
+// term) and fills the term's record directory like tile_dir_kernel fills the word directory.
+#define REC_BLOCK 1024
+__device__ __forceinline__ u32 slot_of_word(const u64 *__restrict__ term_off_sorted, u32 n_slots, u64 i) {
+    u32 lo = 0, hi = n_slots;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (term_off_sorted[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+rec_count_kernel(const u64 *__restrict__ words, u64 n_words, const u64 *__restrict__ term_off_sorted, u32 n_slots,
+                 u32 *__restrict__ bcount) {
+    __shared__ u32 s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    u32 mine = 0;
+    for (int e = 0; e < REC_BLOCK / 256; e++) {
+        const u64 i = (u64)blockIdx.x * REC_BLOCK + e * 256 + threadIdx.x;
+        if (i >= n_words) break;
+        const u64 start = term_off_sorted[slot_of_word(term_off_sorted, n_slots, i)];
+        if (i == start || (words[i] >> SA_KEY_SHIFT) != (words[i - 1] >> SA_KEY_SHIFT)) mine++;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) bcount[blockIdx.x] = s_cnt;
+}
+
+// exclusive scan of u64-accumulated u32 counts by ONE CTA (n ~ 1e6 entries: a few hundred microseconds)
+__global__ void __launch_bounds__(1024)
+rec_scan_kernel(const u32 *__restrict__ bcount, u64 *__restrict__ bbase, u32 n) {
+    __shared__ u64 warp_sums[32];
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 b0 = 0; b0 < n; b0 += 1024) {
+        const u32 i = b0 + threadIdx.x;
+        const u64 v = i < n ? bcount[i] : 0;
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        u64 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        u64 wbase = 0, tot = 0;
+        for (int w = 0; w < 32; w++) {
+            if (w < (int)warp) wbase += warp_sums[w];
+            tot += warp_sums[w];
+        }
+        const u64 c = carry;
+        if (i < n) bbase[i] = c + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rec_write_kernel(const u64 *__restrict__ words, u64 n_words, const u64 *__restrict__ term_off_sorted,
+                 const u64 *__restrict__ slot_len, const u64 *__restrict__ slot_dir_off,
+                 const u64 *__restrict__ slot_rec_off, const u64 *__restrict__ slot_head_base,
+                 const u32 *__restrict__ slot_df, u32 n_slots, const u64 *__restrict__ bbase,
+                 u32 *__restrict__ recs, u32 *__restrict__ rec_dir, u64 doc_base, u32 n_tiles) {
+    __shared__ u32 s_warp[8];
+    __shared__ u32 s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = 0; e < REC_BLOCK / 256; e++) {
+        const u64 i = (u64)blockIdx.x * REC_BLOCK + e * 256 + threadIdx.x;
+        bool head = false;
+        u32 slot = 0;
+        u64 start = 0, w = 0;
+        if (i < n_words) {
+            slot = slot_of_word(term_off_sorted, n_slots, i);
+            start = term_off_sorted[slot];
+            w = words[i];
+            head = (i == start) || ((w >> SA_KEY_SHIFT) != (words[i - 1] >> SA_KEY_SHIFT));
+        }
+        // rank of this head among the block's heads (block-wide exclusive scan of the head flags)
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        u32 before = s_run;
+        for (unsigned x = 0; x < warp; x++) before += s_warp[x];
+        u32 round_total = 0;
+        for (unsigned x = 0; x < 8; x++) round_total += s_warp[x];
+        const u64 g = bbase[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));   // global head rank
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += round_total;
+        if (i < n_words && slot_dir_off[slot] != SA_NO_DIR) {
+            const u64 len = slot_len[slot];
+            const u64 doc = (w >> SA_KEY_SHIFT) - doc_base;
+            const u32 t_i = (u32)(doc / SA_TILE_DOCS);
+            u32 *d = rec_dir + slot_dir_off[slot];
+            if (head) {
+                const u32 rank = (u32)(g - slot_head_base[slot]);                     // within the term
+                u32 tf = 0;
+                for (u64 j = i; j < start + len; j++) {                                // the doc's run of words
+                    const u64 w2 = words[j];
+                    if ((w2 >> SA_KEY_SHIFT) != (w >> SA_KEY_SHIFT)) break;
+                    tf += (u32)__popcll(w2 & SA_LSB_MASK);
+                }
+                recs[slot_rec_off[slot] + rank] = ((u32)(doc % SA_TILE_DOCS) << SA_REC_TF_BITS) | (tf & SA_REC_TF_MASK);
+                if (i == start) {
+                    for (u32 t = 0; t <= t_i && t <= n_tiles; t++) d[t] = 0;
+                } else {
+                    const u32 t_p = (u32)(((words[i - 1] >> SA_KEY_SHIFT) - doc_base) / SA_TILE_DOCS);
+                    for (u32 t = t_p + 1; t <= t_i && t <= n_tiles; t++) d[t] = rank;
+                }
+            }
+            if (i == start + len - 1)
+                for (u32 t = t_i + 1; t <= n_tiles; t++) d[t] = slot_df[slot];
+        }
+    }
+}
+
 extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
                                const uint64_t *term_offsets, const uint64_t *term_lengths, uint32_t n_terms,
                                const float *doc_lens, uint64_t n_docs, uint64_t doc_base,
@@ -217,7 +341,50 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
             CREATE_CUDA(cudaGetLastError());
             ix->stats.total_launches++;
         }
-        CREATE_CUDA(cudaStreamSynchronize(ix->stream));
+        CREATE_CUDA(cudaStreamSynchronize(ix->stream));         // h_df is final from here on
+        // tf table for the terms that have a directory (the long lists: that is where the scan's time goes)
+        static const bool no_tf_table = getenv("SA_NO_TF_TABLE") && atoi(getenv("SA_NO_TF_TABLE")) != 0;
+        ix->h_rec_off.assign(n_terms, SA_NO_DIR);
+        if (dir_words && !no_tf_table) {
+            std::vector<u64> slot_rec(n_slots, SA_NO_DIR), slot_head_base(n_slots, 0);
+            std::vector<u32> slot_df(n_slots, 0);
+            u64 total_recs = 0, heads = 0;
+            for (u32 sI = 0; sI < n_slots; sI++) {
+                const u32 t = term_of_slot[sI];
+                slot_head_base[sI] = heads;
+                slot_df[sI] = ix->h_df[t];
+                heads += ix->h_df[t];
+                if (slot_dir[sI] != SA_NO_DIR) {
+                    slot_rec[sI] = total_recs;
+                    ix->h_rec_off[t] = total_recs;
+                    total_recs += ((u64)ix->h_df[t] + 3) / 4 * 4;          // 16-byte aligned record runs
+                }
+            }
+            const u32 n_rblocks = (u32)((n_words + REC_BLOCK - 1) / REC_BLOCK);
+            u32 *d_bcount = nullptr, *d_slot_df = nullptr;
+            u64 *d_bbase = nullptr, *d_slot_rec = nullptr, *d_slot_hb = nullptr;
+            CREATE_CUDA(cudaMalloc(&ix->d_recs, (total_recs + 8) * sizeof(u32)));
+            CREATE_CUDA(cudaMemsetAsync(ix->d_recs, 0, (total_recs + 8) * sizeof(u32), ix->stream));
+            CREATE_CUDA(cudaMalloc(&ix->d_rec_dir, dir_words * sizeof(u32)));
+            ix->device_bytes += (total_recs + 8) * sizeof(u32) + dir_words * sizeof(u32);
+            CREATE_CUDA(cudaMalloc(&d_bcount, (size_t)n_rblocks * sizeof(u32)));
+            CREATE_CUDA(cudaMalloc(&d_bbase, (size_t)n_rblocks * sizeof(u64)));
+            CREATE_CUDA(cudaMalloc(&d_slot_rec, n_slots * sizeof(u64)));
+            CREATE_CUDA(cudaMalloc(&d_slot_hb, n_slots * sizeof(u64)));
+            CREATE_CUDA(cudaMalloc(&d_slot_df, n_slots * sizeof(u32)));
+            CREATE_CUDA(cudaMemcpyAsync(d_slot_rec, slot_rec.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+            CREATE_CUDA(cudaMemcpyAsync(d_slot_hb, slot_head_base.data(), n_slots * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+            CREATE_CUDA(cudaMemcpyAsync(d_slot_df, slot_df.data(), n_slots * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+            rec_count_kernel<<<n_rblocks, 256, 0, ix->stream>>>(ix->d_words, n_words, d_off, n_slots, d_bcount);
+            rec_scan_kernel<<<1, 1024, 0, ix->stream>>>(d_bcount, d_bbase, n_rblocks);
+            rec_write_kernel<<<n_rblocks, 256, 0, ix->stream>>>(ix->d_words, n_words, d_off, d_slot_len, d_slot_dir, d_slot_rec,
+                                                                d_slot_hb, d_slot_df, n_slots, d_bbase, ix->d_recs, ix->d_rec_dir,
+                                                                doc_base, n_tiles);
+            CREATE_CUDA(cudaGetLastError());
+            ix->stats.total_launches += 3;
+            CREATE_CUDA(cudaStreamSynchronize(ix->stream));
+            cudaFree(d_bcount); cudaFree(d_bbase); cudaFree(d_slot_rec); cudaFree(d_slot_hb); cudaFree(d_slot_df);
+        }
         cudaFree(d_off);
         cudaFree(d_slot);
         cudaFree(d_slot_len);
@@ -241,6 +408,8 @@ extern "C" int sa_index_destroy(sa_index *ix) {
     cudaFree(ix->d_doc_lens);
     cudaFree(ix->d_df);
     cudaFree(ix->d_tile_dir);
+    cudaFree(ix->d_recs);
+    cudaFree(ix->d_rec_dir);
     cudaFree(ix->d_norm);
     cudaFree(ix->d_rows);
     cudaFree(ix->d_row_mask);
@@ -351,6 +520,7 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
     tq.word_off = term_id == SA_NO_TERM ? 0 : ix->h_off[term_id];
     tq.n_words = term_id == SA_NO_TERM ? 0 : ix->h_len[term_id];
     tq.dir_off = term_id == SA_NO_TERM ? SA_NO_DIR : ix->h_dir_off[term_id];
+    tq.rec_off = (term_id == SA_NO_TERM || ix->h_rec_off.empty()) ? SA_NO_DIR : ix->h_rec_off[term_id];
     tq.idf = p.idf;
     const u64 *words = ix->d_words;
     bool filter = !(min_payload == 0 && max_payload == SA_ALL_BITS);
@@ -362,6 +532,7 @@ static int single_term(sa_index *ix, uint32_t term_id, int mode, const Bm25Param
         tq.word_off = offs[0];
         tq.n_words = lens[0];
         tq.dir_off = SA_NO_DIR;
+        tq.rec_off = SA_NO_DIR;
         filter = false;
     }
     SA_CUDA(cudaMemcpyAsync(ix->queries.p, &tq, sizeof(tq), cudaMemcpyHostToDevice, ix->stream));
@@ -448,6 +619,7 @@ static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
     tq.word_off = t == SA_NO_TERM ? 0 : ix->h_off[t];
     tq.n_words = t == SA_NO_TERM ? 0 : ix->h_len[t];
     tq.dir_off = t == SA_NO_TERM ? SA_NO_DIR : ix->h_dir_off[t];
+    tq.rec_off = (t == SA_NO_TERM || ix->h_rec_off.empty()) ? SA_NO_DIR : ix->h_rec_off[t];
     tq.idf = idf;
     return tq;
 }

@@ -71,7 +71,14 @@ term_tile_kernel(const TermBatchArgs a) {
     for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
         reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
     u32 lo, hi;
-    if (tq.dir_off != SA_NO_DIR) {                                    // CTA-uniform
+    // tf-table path (CTA-uniform): the term has (doc, tf) records and nothing has to look inside the words
+    const bool use_recs = !FILTER && !ALL_DOCS && a.recs != nullptr && tq.rec_off != SA_NO_DIR && tq.dir_off != SA_NO_DIR;
+    if (use_recs) {
+        const u32 *dir = a.rec_dir + tq.dir_off + tile;
+        lo = __ldg(dir);
+        hi = __ldg(dir + 1);
+        __syncthreads();
+    } else if (tq.dir_off != SA_NO_DIR) {                             // CTA-uniform
         const u32 *dir = a.tile_dir + tq.dir_off + tile;
         lo = __ldg(dir);
         hi = __ldg(dir + 1);
@@ -93,7 +100,8 @@ term_tile_kernel(const TermBatchArgs a) {
     // round trip per pass.  A doc's head reads its norm from the tile and stores the score NEGATED:
     // norms are > 0 here and scores >= +0, so the sign bit tells a score (set) from a leftover norm
     // (clear), which the flush turns into 0.
-    const bool staged_norm = MODE == TERM_MODE_SCORE && !ALL_DOCS && (hi - lo) >= a.staged_norm_min_words;
+    const bool staged_norm = MODE == TERM_MODE_SCORE && !ALL_DOCS &&
+                             (hi - lo) >= (use_recs ? (u32)SA_STAGED_NORM_MIN_RECS : a.staged_norm_min_words);
     bool norm_ready = !staged_norm;
     if (staged_norm) {
         const float4 *__restrict__ n4 = reinterpret_cast<const float4 *>(a.norm + tile_doc0);
@@ -185,6 +193,43 @@ term_tile_kernel(const TermBatchArgs a) {
             }
         }
     };
+    if (use_recs) {
+        // 2'. tf-table path: one u32 record per matching doc, (doc - tile_doc0) << 19 | tf, in doc order.  Every
+        //     lane takes FOUR records with one 16-byte load (record runs start 16-byte aligned; the slice is
+        //     widened to whole quads and the strangers masked); no run detection, no shuffles, no popcount.
+        const u32 *__restrict__ recs = a.recs + tq.rec_off;
+        for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
+            const u32 i = base + tid * 4;
+            uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+            if (i < hi) r4 = __ldg(reinterpret_cast<const uint4 *>(recs + i));
+            const u32 rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            float nr4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+            if (MODE == TERM_MODE_SCORE && !staged_norm) {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (i + e >= lo && i + e < hi) nr4[e] = __ldg(norm + (rr[e] >> SA_REC_TF_BITS));
+            }
+            if (!norm_ready) {                             // CTA-uniform: first pass of a staged tile
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();
+                norm_ready = true;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (i + e < lo || i + e >= hi) continue;
+                const u32 rel = rr[e] >> SA_REC_TF_BITS, tf = rr[e] & SA_REC_TF_MASK;
+                float v = (float)tf;
+                if (MODE == TERM_MODE_SCORE) {
+                    v = 0.0f;
+                    if (tf) {
+                        v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : nr4[e], tq.idf);
+                        my_max = max(my_max, __float_as_uint(v));
+                    }
+                }
+                s_out[rel] = staged_norm ? -v : v;
+            }
+        }
+    } else {
     // CTA-uniform schedule: big slices in 4-window passes, the remainder (and small tiles) in
     // single-window passes so sparse tiles do not pay for empty windows.
     u32 base = lo;
@@ -195,6 +240,7 @@ term_tile_kernel(const TermBatchArgs a) {
     while (base < hi) {
         windows(std::integral_constant<int, 1>{}, base);
         base += WIN;
+    }
     }
 
     // 3. top-k.  A tile with no more words than candidate slots needs no bound: every positive
@@ -266,6 +312,9 @@ term_tile_kernel(const TermBatchArgs a) {
     if (k) {
         if (cand_max) atomicMax(&s_tile_max, cand_max);
         __syncthreads();
+        if (s_ncand > a.topk.slots && !(ALL_DOCS && MODE == TERM_MODE_SCORE))    // CTA-uniform: ties at the bound
+            tile_collect_ties_retry(s_out, staged_norm, __float_as_uint(thr_f), a.topk, my_cand, tile_doc0, s_top,
+                                    &s_ncand, &s_tile_max);
         if (tid == 0) {
             const u32 n = s_ncand;
             const u64 t_idx = (u64)q * a.topk.n_tiles + tile;
@@ -401,6 +450,8 @@ int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
         a.staged_norm_min_words = env_thresh >= 0 ? (u32)env_thresh : SA_STAGED_NORM_MIN_WORDS;
     }
     a.tile_dir = ix->d_tile_dir;
+    a.recs = (a.words == ix->d_words) ? ix->d_recs : nullptr;     // the tf table describes the index's own lists only
+    a.rec_dir = ix->d_rec_dir;
     a.norm = ix->d_norm;
     const bool sparse_score = (a.mode == TERM_MODE_SCORE) && a.bm25.sparse_ok;
     if (sparse_score) {

@@ -6,6 +6,7 @@
 #define SA_TERM_UNROLL 4           // 30-word windows loaded per warp before processing
 #define SA_TERM_THREADS 256
 #define SA_STAGED_NORM_MIN_WORDS 1024   // tiles with at least this many posting words stage the tile's norms (sa_term.cu)
+#define SA_STAGED_NORM_MIN_RECS 768     // ... or this many (doc, tf) records on the tf-table path
 #define SA_TOPK_MAX 32             // warp-level threshold estimation handles k <= 32
 
 enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
@@ -27,6 +28,8 @@ struct TermBatchArgs {
     const float *doc_lens;
     const float *norm;          // per-doc BM25 length norm (padded to a tile multiple), SCORE mode
     const u32 *tile_dir;        // tile directories (see sa_index::d_tile_dir)
+    const u32 *recs;            // per-term (doc, tf) records (sa_index::d_recs) or NULL
+    const u32 *rec_dir;         // record directories, same offsets as tile_dir
     u64 n_docs;
     u64 doc_base;
     const TermQuery *queries;   // [Q]
@@ -96,6 +99,66 @@ __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k)
 }
 
 
+// Candidate-slot overflow caused by TIES at the tile bound (BM25 scores are a function of (tf, doc_len) only, so
+// exact ties among thousands of docs are normal): the tile is still in shared memory, so the CTA collects
+// again, now breaking ties the way the final ranking does -- lower doc id first.  Scores above the bound are
+// all kept; of the docs AT the bound only those with a local index <= the k-th smallest such index (a bound
+// derived from the threads' smallest tied docs, which are distinct docs) are kept: a superset of what the
+// top-k can take from this tile.  `negated`: the tile holds -score for scored docs and a positive leftover
+// norm elsewhere (term kernel, staged norms).  All SA_TERM_THREADS threads call; returns with the slots,
+// *s_ncand and *s_tile_max rewritten (the caller publishes them).  Still more than `slots` -> the caller
+// flags the query for the exact host-side re-run, as before.
+__device__ __forceinline__ void tile_collect_ties_retry(const float *s_out, bool negated, u32 thr_bits, const TopkCtx &t,
+                                                        u64 *__restrict__ my_cand, u32 tile_doc0, u32 *s_top,
+                                                        u32 *s_ncand, u32 *s_tile_max) {
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float thr_f = __uint_as_float(thr_bits);
+    u32 best = 0;                                   // 0xFFFFFFFF - smallest tied local doc of this thread (0 = none)
+#pragma unroll
+    for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
+        const unsigned g = tid + jj * SA_TERM_THREADS;
+        const float4 raw = reinterpret_cast<const float4 *>(s_out)[g];
+        const float vs[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float v = negated ? (__float_as_int(vs[e]) < 0 ? -vs[e] : 0.0f) : vs[e];
+            if (v == thr_f) best = max(best, 0xFFFFFFFFu - (g * 4 + e));
+        }
+    }
+    const u32 M = (t.k <= 10) ? 4u : 8u;
+    __syncthreads();                                // s_top may still be read by a slow warp of the first pass
+    {
+        u32 v = best;
+        for (u32 r = 0; r < M; r++) {
+            u32 m = warp_pop_max(v);
+            if (lane == r) s_top[warp * 8 + r] = m;
+        }
+    }
+    if (tid == 0) { *s_ncand = 0; *s_tile_max = 0; }
+    __syncthreads();
+    const u32 kth = cta_kth_bound(s_top, t.k);      // 0: fewer than k threads hold a tie -> keep every tie
+    const u32 doc_bound = kth ? 0xFFFFFFFFu - kth : 0xFFFFFFFFu;
+    u32 cand_max = 0;
+#pragma unroll
+    for (int jj = 0; jj < SA_TILE_DOCS / SA_TERM_THREADS / 4; jj++) {
+        const unsigned g = tid + jj * SA_TERM_THREADS;
+        const float4 raw = reinterpret_cast<const float4 *>(s_out)[g];
+        const float vs[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float v = negated ? (__float_as_int(vs[e]) < 0 ? -vs[e] : 0.0f) : vs[e];
+            if (v > thr_f || (v == thr_f && g * 4 + e <= doc_bound)) {
+                u32 slot = atomicAdd(s_ncand, 1u);
+                if (slot < t.slots)
+                    my_cand[slot] = ((u64)__float_as_uint(v) << 32) | (u64)(0xFFFFFFFFu - (tile_doc0 + g * 4 + e));
+                cand_max = max(cand_max, __float_as_uint(v));
+            }
+        }
+    }
+    if (cand_max) atomicMax(s_tile_max, cand_max);
+    __syncthreads();
+}
+
 // Flush one shared-memory score tile to its dense row with 16-byte streaming stores and, on the way,
 // collect the tile's top-k candidates (private slots, count, maximum): the same step the term kernel
 // ends with, shared with the phrase kernel.  `my_max` = largest score bits this thread put into the
@@ -147,6 +210,8 @@ __device__ __forceinline__ void flush_tile_collect(const float *s_out, float *__
     if (k) {
         if (cand_max) atomicMax(s_tile_max, cand_max);
         __syncthreads();
+        if (*s_ncand > t.slots)                                      // CTA-uniform: ties at the bound (see above)
+            tile_collect_ties_retry(s_out, false, __float_as_uint(thr_f), t, my_cand, tile_doc0, s_top, s_ncand, s_tile_max);
         if (tid == 0) {
             const u32 n = *s_ncand;
             const u64 t_idx = (u64)row * t.n_tiles + tile;
