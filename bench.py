@@ -514,7 +514,13 @@ def bench_ours(args, rank, world):
     # ---- roofline of the dominant kernel (per-launch CUDA events, async)
     W = host.term_lengths[term_ids].astype(np.float64)
     dfl = o.df_local.astype(np.float64)
-    alg_q = 8.0 * W + 4.0 * dfl[term_ids] + 4.0 * host.n_docs          # per query, this shard
+    # per query, this shard.  Lists with a tile directory are scanned through the tf table the index
+    # builds at upload -- one 4-byte (doc, tf) record per matching doc instead of the 8-byte posting words -- so
+    # their posting term is 4*df ("its actual record size"); short lists are still scanned as words (8*W).
+    n_tiles = (host.n_docs + 8191) // 8192
+    has_table = (W >= max(1024, n_tiles // 2)) & (os.environ.get("SA_NO_TF_TABLE", "0") in ("", "0"))
+    post_bytes = np.where(has_table, 4.0 * dfl[term_ids], 8.0 * W)
+    alg_q = post_bytes + 4.0 * dfl[term_ids] + 4.0 * host.n_docs
     prof_steps = min(args.steps, 5)
     st = o.profiled(prof_steps)
     term_ms = st.term_kernel_ms / prof_steps
@@ -525,7 +531,10 @@ def bench_ours(args, rank, world):
     roofline = {"bound": "hbm", "kernel": "term_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": float(alg_q.sum()) / launches_per_step,
-                "algorithmic_bytes": "8*W + 4*df + 4*N per query (SURVEY 8d), summed over the launch's queries",
+                "algorithmic_bytes": "postings + 4*df (norms) + 4*N (dense row) per query (SURVEY 8d), summed over the "
+                                     "launch's queries; postings = 4*df for lists scanned through the upload-time "
+                                     "(doc, tf) record table, 8*W for short lists scanned as words",
+                "tf_table_queries": int(np.count_nonzero(has_table)),
                 "avg_launch_ms": term_ms / launches_per_step, "launches_per_step": launches_per_step,
                 "topk_select_ms_per_step": st.topk_kernel_ms / prof_steps,
                 "kernel_share_of_step": term_ms / (dev_ms / args.steps)}
@@ -542,7 +551,10 @@ def bench_ours(args, rank, world):
             o.execute()
         stb = o.profiled(3)
         ms_b = stb.term_kernel_ms / 3
+        b_docs = np.empty((len(sel), k), dtype=np.uint32)
+        b_scores = np.empty((len(sel), k), dtype=np.float32)
         buckets.append({"df_over_n": p, "queries": int(len(sel)), "us_per_query": 1e3 * ms_b / len(sel),
+                        "topk_overflow_reruns": int(o.download(b_docs, b_scores)),
                         "achieved": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9,
                         "frac": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9 / peak})
     roofline["by_df_bucket"] = buckets

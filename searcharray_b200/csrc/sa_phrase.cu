@@ -28,6 +28,7 @@
 #include "sa_phrase.cuh"
 #include "sa_span.cuh"
 #include "sa_term.cuh"
+#include "sa_tma.cuh"
 
 int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bool use_rows,
                     u64 pay_lo, u64 pay_hi, bool use_payload, std::vector<u64> &offs, std::vector<u64> &lens);
@@ -309,67 +310,94 @@ __device__ void and_min(u64 *__restrict__ cur, u64 n_cur, const u64 *__restrict_
 
 struct ChainResult { u64 *docs; u64 n_docs; u64 *cont; u64 n_cont; };
 
-__global__ void __launch_bounds__(PT)
-phrase_kernel(const PhraseArgs a) {
-    __shared__ StepShared S;
-    __shared__ u64 s_lo[SA_MAX_PHRASE_TERMS], s_n[SA_MAX_PHRASE_TERMS];
-    __shared__ u64 s_slab;
-    __shared__ int s_ok;
-    __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
-    __shared__ u32 s_top[(PT / 32) * 8];
-    __shared__ u32 s_ncand, s_tile_max;
+// Shared state of one CTA of the phrase kernels.
+struct PhraseShared {
+    StepShared S;
+    u64 lo[SA_MAX_PHRASE_TERMS], n[SA_MAX_PHRASE_TERMS];        // this CTA's doc-range chunk: slice of every term's list
+    const u64 *ptr[SA_MAX_PHRASE_TERMS];                        // current segment: where each term's slice is read from
+    u64 seg_lo[SA_MAX_PHRASE_TERMS], seg_n[SA_MAX_PHRASE_TERMS];
+    u64 slab;
+    int ok;
+    u32 seg_te, any_staged, work;
+    __align__(16) float tile[SA_TILE_DOCS];
+    u32 top[(PT / 32) * 8];
+    u32 ncand, tile_max;
+    __align__(8) u64 bar;
+};
 
-    // grid = (queries, chunks): neighbouring CTAs belong to different queries (see term_tile_kernel)
-    const u32 q = blockIdx.x;
-    const u32 chunk = blockIdx.y;
+// One (query, doc-range chunk) work item.
+//
+// STAGED == false -- the search regime (|shortest list| << |the others|): the chain runs once over the whole
+//   chunk; a step's driver elements binary-search the other list in global memory, which skips most of it.
+// STAGED == true -- the merge regime (balanced lists; chosen per query by the host, sa_phrase_is_staged): the
+//   chunk is cut into SEGMENTS of whole tiles whose posting slices fit in the CTA's staging buffer; one elected
+//   thread copies every term's slice of the segment into shared memory with TMA bulk copies
+//   (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes), the CTA waits on the mbarrier, and the
+//   same chain then runs with every search hitting shared memory: each list is read from HBM exactly once,
+//   sequentially (the 8 * sum(W) of B_phrase), and the continuation lists stay in a per-CTA slab that lives in
+//   L2.  A slice that does not fit (a tile of a very dense term) is simply read from global memory.
+template <bool STAGED>
+__device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, PhraseShared &P, u64 *stage,
+                            u32 &bar_phase, u64 *cta_slab, u64 cta_slab_cap) {
     const PhraseQuery &pq = a.queries[q];
     const u32 n_terms = pq.n_terms;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 d0 = a.doc_base + (u64)chunk * a.docs_per_chunk;
     const u64 dend = a.doc_base + a.n_docs;
-    if (d0 >= dend) return;                    // (grid is sized so this does not happen)
+    if (d0 >= dend) return;                    // (grids are sized so this does not happen)
     const u64 d1 = min(d0 + a.docs_per_chunk, dend);
-    ChainResult fin;
-    fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
-    bool run = true;
+    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    StepShared &S = P.S;
 
-    // 1. every term's slice for this doc range
+    // 1. every term's slice for this CTA's doc range (tile directory when the list has one)
+    __syncthreads();                            // (persistent CTAs: the previous work item is done with P)
     for (u32 t = warp; t < n_terms; t += PT / 32) {
         const u64 *lst = a.words + pq.off[t];
-        u64 lo = warp_lower_bound_shifted(lst, 0, pq.len[t], d0, SA_KEY_SHIFT);
-        u64 hi = warp_lower_bound_shifted(lst, lo, pq.len[t], d1, SA_KEY_SHIFT);
-        if (lane == 0) { s_lo[t] = lo; s_n[t] = hi - lo; }
+        u64 lo, hi;
+        if (pq.dir_plus1[t] && a.tile_dir) {
+            const u32 *dir = a.tile_dir + (pq.dir_plus1[t] - 1);
+            lo = __ldg(dir + tile0);
+            hi = __ldg(dir + tile1);
+        } else {
+            lo = warp_lower_bound_shifted(lst, 0, pq.len[t], d0, SA_KEY_SHIFT);
+            hi = warp_lower_bound_shifted(lst, lo, pq.len[t], d1, SA_KEY_SHIFT);
+        }
+        if (lane == 0) { P.lo[t] = lo; P.n[t] = hi - lo; }
     }
     __syncthreads();
     u64 cap = 0, widest = 0;
     for (u32 t = 0; t < n_terms; t++) {
-        cap = max(cap, s_n[t]);
-        if (s_n[t]) widest++;
+        cap = max(cap, P.n[t]);
+        if (P.n[t]) widest++;
     }
     // A chunk where fewer than two terms occur has no pairs at any step.  (A chunk that merely
     // misses ONE term must still run its earlier steps: their pairs count towards the global
     // same-term decision of the reference.)
-    if (widest < 2) run = false;
+    bool run = widest >= 2;
     cap += 2;
 
-    // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers
-    if (tid == 0) {
-        s_ok = 1;
-        s_slab = 0;
+    // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers.  Bound: a step's continuation words carry
+    //    distinct headers of the NEW term's slice and its (doc, count) entries come from distinct driver elements,
+    //    so `longest slice + 2` entries per buffer always suffice.
+    if (STAGED) {
+        cap = cta_slab_cap;                    // per-CTA slab, sized by the host from the per-tile maxima
+        if (tid == 0) { P.ok = 1; P.slab = 0; }
+    } else if (tid == 0) {
+        P.ok = 1;
+        P.slab = 0;
         if (run) {
             unsigned long long need = 6ull * cap;
             unsigned long long at = atomicAdd(a.arena_used, need);
-            s_ok = (at + need <= a.arena_cap);
-            s_slab = at;
-            if (!s_ok) atomicExch(&a.stats[q].overflow, 1u);
+            P.ok = (at + need <= a.arena_cap);
+            P.slab = at;
+            if (!P.ok) atomicExch(&a.stats[q].overflow, 1u);
         }
     }
     __syncthreads();
-    if (!s_ok) run = false;
-    u64 *contA = a.arena + s_slab, *contB = contA + cap;
+    if (!P.ok) run = false;
+    u64 *contA = (STAGED ? cta_slab : a.arena + P.slab), *contB = contA + cap;
     u64 *docsA = contB + cap, *docsB = docsA + cap, *docsL = docsB + cap, *docsR = docsL + cap;
-
-    auto slice = [&](u32 t) { return a.words + pq.off[t] + s_lo[t]; };
 
     // Runs one chain over terms [ta, tb).  lr: left-to-right (cont = RHS) else right-to-left.
     auto run_chain = [&](u32 ta, u32 tb, bool lr, u64 *final_docs) -> ChainResult {
@@ -378,8 +406,8 @@ phrase_kernel(const PhraseArgs a) {
         res.n_docs = 0;
         res.cont = contA;
         res.n_cont = 0;
-        const u64 *carry = lr ? slice(ta) : slice(tb - 1);
-        u64 n_carry = lr ? s_n[ta] : s_n[tb - 1];
+        const u64 *carry = lr ? P.ptr[ta] : P.ptr[tb - 1];
+        u64 n_carry = lr ? P.seg_n[ta] : P.seg_n[tb - 1];
         u64 *cont_bufs[2] = {contA, contB};
         u64 *doc_bufs[2] = {docsA, docsB};
         int flip = 0;
@@ -389,8 +417,8 @@ phrase_kernel(const PhraseArgs a) {
         for (u32 s = 0; s < n_steps; s++) {
             const u32 tnew = lr ? (ta + 1 + s) : (tb - 2 - s);     // also the step id
             const bool same = (pq.same_guess >> tnew) & 1u;
-            const u64 *other = slice(tnew);
-            const u64 n_other = s_n[tnew];
+            const u64 *other = P.ptr[tnew];
+            const u64 n_other = P.seg_n[tnew];
             if (n_carry == 0 || n_other == 0) {   // no pairs from here on in this doc range
                 res.n_docs = 0;
                 res.n_cont = 0;
@@ -432,91 +460,212 @@ phrase_kernel(const PhraseArgs a) {
         return res;
     };
 
-    if (run) {
-    if (pq.mode == SA_PHRASE_MODE_LR) {
-        fin = run_chain(0, n_terms, true, docsL);
-    } else if (pq.mode == SA_PHRASE_MODE_RL) {
-        fin = run_chain(0, n_terms, false, docsL);
-    } else {
-        // both chains always run (their pair statistics feed the speculation check)
-        ChainResult left = run_chain(0, pq.split, true, docsL);
-        fin = run_chain(pq.split, n_terms, false, docsR);
-        if (left.n_docs == 0) fin.n_docs = 0;
-        and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
-    }
-
-    }
-    // optional dump for the per-op parity export (single chunk)
-    if (a.dump.cont) {
-        for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
-        for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
-        if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
-    }
-
-    // 3. materialise the dense vector of this doc range tile by tile (phrase_freqs[ids] = counts,
-    //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
-    //    streaming stores; the same pass collects the tile's top-k candidates.
     float *out = a.out + (u64)q * a.out_stride;
     Bm25Params p = a.bm25;
     p.idf = pq.idf;
     const u32 row = a.topk_row0 + q;
-    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
-    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
-    // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
-    // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
-    // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
-    u64 cur = 0;
-    u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
-    for (u32 tile = tile0; tile < tile1; tile++) {
-        const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
-        if (next_doc >= t_abs1) {
-            float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
-            if (a.topk.k && tid == 0) {
-                const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
-                a.topk.tile_cnt[t_idx] = 0;
-                a.topk.tile_max[t_idx] = 0;
+
+    u32 ts = tile0;
+    while (ts < tile1) {
+        // ---- the segment [ts, te): the whole chunk (search regime) or as many tiles as the staging buffer holds
+        u32 te = tile1;
+        if (STAGED && run) {
+            if (warp == 0) {
+                const bool has = lane < n_terms;
+                const u32 *dir = (has && pq.dir_plus1[lane] && a.tile_dir) ? a.tile_dir + (pq.dir_plus1[lane] - 1) : nullptr;
+                const u32 fixed = (has && !dir) ? (u32)min(P.n[lane], (u64)0x7FFFFFFFu) : 0u;
+                const u32 base = dir ? __ldg(dir + ts) : 0u;
+                u32 best = ts + 1;
+                for (u32 cand = ts + 1; cand <= tile1; cand++) {
+                    u32 mine = has ? ((dir ? __ldg(dir + cand) - base : fixed) + 4u) : 0u;      // + alignment slack
+                    const u32 sum = __reduce_add_sync(0xffffffffu, mine);
+                    if (cand > ts + 1 && sum > a.stage_words) break;
+                    best = cand;
+                    if (sum > a.stage_words) break;
+                }
+                if (lane == 0) P.seg_te = best;
             }
-            continue;
+            __syncthreads();
+            te = P.seg_te;
         }
-        // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
-        const u64 m0 = cur;
-        u64 lo = cur + 1, hi = fin.n_docs, st = 1;
-        while (lo < hi) {
-            const u64 probe = min(lo + st - 1, hi - 1);
-            if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
-            else { hi = probe; break; }
+        const u64 seg_d0 = a.doc_base + (u64)ts * SA_TILE_DOCS;
+        const u64 seg_d1 = min(a.doc_base + (u64)te * SA_TILE_DOCS, dend);
+        // ---- per-term slices of the segment
+        if (STAGED && run) {
+            for (u32 t = warp; t < n_terms; t += PT / 32) {
+                const u64 *lst = a.words + pq.off[t];
+                u64 lo, hi;
+                if (pq.dir_plus1[t] && a.tile_dir) {
+                    const u32 *dir = a.tile_dir + (pq.dir_plus1[t] - 1);
+                    lo = __ldg(dir + ts);
+                    hi = __ldg(dir + te);
+                } else {
+                    lo = warp_lower_bound_shifted(lst, P.lo[t], P.lo[t] + P.n[t], seg_d0, SA_KEY_SHIFT);
+                    hi = warp_lower_bound_shifted(lst, lo, P.lo[t] + P.n[t], seg_d1, SA_KEY_SHIFT);
+                }
+                if (lane == 0) { P.seg_lo[t] = lo; P.seg_n[t] = hi - lo; }
+            }
+            __syncthreads();
+            // ---- stage: one elected thread arms the barrier and issues one bulk copy per term
+            if (tid == 0) {
+                u32 at = 0, total = 0, seg_ok = 1;
+                bool st[SA_MAX_PHRASE_TERMS];
+                u32 so[SA_MAX_PHRASE_TERMS];
+                for (u32 t = 0; t < n_terms; t++) {
+                    const u32 n = (u32)P.seg_n[t];
+                    const u32 wds = sa_stage_bytes(a.words + pq.off[t], P.seg_lo[t], n) / 8u;
+                    st[t] = n > 0 && P.seg_n[t] < 0x7FFFFFFFull && at + wds <= a.stage_words;
+                    so[t] = at;
+                    if (st[t]) { at += wds; total += wds * 8u; }
+                    if (P.seg_n[t] + 2 > cap) seg_ok = 0;         // cannot happen: the slab is sized from the per-tile maxima
+                }
+                if (total) {
+                    sa_fence_proxy_async();
+                    sa_mbar_expect_tx(&P.bar, total);
+                }
+                for (u32 t = 0; t < n_terms; t++) {
+                    const u64 *lst = a.words + pq.off[t];
+                    if (st[t]) {
+                        const u32 head = sa_stage_issue(stage + so[t], lst, P.seg_lo[t], (u32)P.seg_n[t], &P.bar);
+                        P.ptr[t] = stage + so[t] + head;
+                    } else {
+                        P.ptr[t] = lst + P.seg_lo[t];
+                    }
+                }
+                P.any_staged = total ? 1u : 0u;
+                if (!seg_ok) { P.ok = 0; atomicExch(&a.stats[q].overflow, 1u); }
+            }
+            __syncthreads();
+            if (P.any_staged) {
+                sa_mbar_wait(&P.bar, bar_phase);
+                bar_phase ^= 1u;
+            }
+        } else {
+            if (tid < n_terms) {
+                P.ptr[tid] = a.words + pq.off[tid] + P.lo[tid];
+                P.seg_n[tid] = P.n[tid];
+            }
+            __syncthreads();
         }
-        while (lo < hi) {
-            const u64 mid = (lo + hi) >> 1;
-            if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+
+        ChainResult fin;
+        fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
+        if (run && P.ok) {
+            if (pq.mode == SA_PHRASE_MODE_LR) {
+                fin = run_chain(0, n_terms, true, docsL);
+            } else if (pq.mode == SA_PHRASE_MODE_RL) {
+                fin = run_chain(0, n_terms, false, docsL);
+            } else {
+                // both chains always run (their pair statistics feed the speculation check)
+                ChainResult left = run_chain(0, pq.split, true, docsL);
+                fin = run_chain(pq.split, n_terms, false, docsR);
+                if (left.n_docs == 0) fin.n_docs = 0;
+                and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
+            }
         }
-        const u64 m1 = lo;
-        cur = m1;
-        next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
+        // optional dump for the per-op parity export (single chunk, search regime)
+        if (!STAGED && a.dump.cont) {
+            for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
+            for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
+            if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
+        }
+
+        // 3. materialise the dense vector of the segment tile by tile (phrase_freqs[ids] = counts,
+        //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
+        //    streaming stores; the same pass collects the tile's top-k candidates.
+        // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
+        // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
+        // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
+        u64 cur = 0;
+        u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
+        for (u32 tile = ts; tile < te; tile++) {
+            const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
+            if (next_doc >= t_abs1) {
+                float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
-            reinterpret_cast<float4 *>(s_tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
-        u32 my_max = 0, my_match = 0;
-        for (u64 i = m0 + tid; i < m1; i += PT) {
-            const u64 e = fin.docs[i];
-            const u32 c = (u32)(e & 0xFFFFFFFFull);
-            if (c == 0) continue;
-            const u64 d = (e >> 32) - a.doc_base;
-            if (d >= a.n_docs) continue;
-            my_match++;
-            const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
-            s_tile[d - (u64)tile * SA_TILE_DOCS] = v;
-            if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+                if (a.topk.k && tid == 0) {
+                    const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                    a.topk.tile_cnt[t_idx] = 0;
+                    a.topk.tile_max[t_idx] = 0;
+                }
+                continue;
+            }
+            // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
+            const u64 m0 = cur;
+            u64 lo = cur + 1, hi = fin.n_docs, st = 1;
+            while (lo < hi) {
+                const u64 probe = min(lo + st - 1, hi - 1);
+                if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
+                else { hi = probe; break; }
+            }
+            while (lo < hi) {
+                const u64 mid = (lo + hi) >> 1;
+                if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+            }
+            const u64 m1 = lo;
+            cur = m1;
+            next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
+#pragma unroll
+            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+                reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            u32 my_max = 0, my_match = 0;
+            for (u64 i = m0 + tid; i < m1; i += PT) {
+                const u64 e = fin.docs[i];
+                const u32 c = (u32)(e & 0xFFFFFFFFull);
+                if (c == 0) continue;
+                const u64 d = (e >> 32) - a.doc_base;
+                if (d >= a.n_docs) continue;
+                my_match++;
+                const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+                P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
+                if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+            }
+            my_match = __reduce_add_sync(0xffffffffu, my_match);
+            if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+            __syncthreads();
+            flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
+                               P.top, &P.ncand, &P.tile_max);
         }
-        my_match = __reduce_add_sync(0xffffffffu, my_match);
-        if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+        __syncthreads();                    // every read of the staged slices / the slab is done before the next segment
+        ts = te;
+    }
+}
+
+__global__ void __launch_bounds__(PT, 4)
+phrase_kernel(const PhraseArgs a) {
+    __shared__ PhraseShared P;
+    // grid = (queries, chunks): neighbouring CTAs belong to different queries (see term_tile_kernel)
+    u32 phase = 0;
+    const u32 q = a.qsel ? a.qsel[blockIdx.x] : blockIdx.x;
+    phrase_work<false>(a, q, blockIdx.y, P, nullptr, phase, nullptr, 0);
+}
+
+// Persistent CTAs (grid = resident CTAs of the device): work items (query, chunk) are claimed with an atomic
+// counter, each CTA keeps its staging buffer (dynamic shared memory), its mbarrier and its scratch slab.
+__global__ void __launch_bounds__(PT)
+phrase_staged_kernel(const PhraseArgs a) {
+    __shared__ PhraseShared P;
+    extern __shared__ __align__(16) u64 s_stage[];
+    if (threadIdx.x == 0) {
+        sa_mbar_init(&P.bar, 1);
+        sa_mbar_fence_init();
+    }
+    __syncthreads();
+    u32 phase = 0;
+    u64 *slab = a.slabs + (u64)blockIdx.x * 6ull * a.slab_cap;
+    const u32 n_work = a.n_sel * a.n_chunks;
+    for (;;) {
         __syncthreads();
-        flush_tile_collect(s_tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
-                           s_top, &s_ncand, &s_tile_max);
+        if (threadIdx.x == 0) P.work = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const u32 w = P.work;
+        if (w >= n_work) break;
+        // consecutive work items belong to different queries (dense and sparse lists interleave on an SM)
+        const u32 q = a.qsel[w % a.n_sel], chunk = w / a.n_sel;
+        phrase_work<true>(a, q, chunk, P, s_stage, phase, slab, a.slab_cap);
     }
 }
 
@@ -530,6 +679,48 @@ int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries) {
     ix->stats.phrase_kernel_launches++;
     ix->stats.total_launches++;
     return SA_OK;
+}
+
+// resident CTAs of phrase_staged_kernel with `stage_words` words of dynamic shared memory
+static int staged_grid(sa_index *ix, u32 stage_words, u32 *ctas_out) {
+    static bool attr_set = false;
+    const size_t dyn = (size_t)stage_words * sizeof(u64);
+    if (!attr_set) {
+        SA_CUDA(cudaFuncSetAttribute(phrase_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    int per_sm = 0;
+    SA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, phrase_staged_kernel, PT, dyn));
+    SA_CHECK(per_sm >= 1, "phrase_staged_kernel does not fit on an SM with %u staged words", stage_words);
+    *ctas_out = (u32)per_sm * (u32)ix->num_sms;
+    return SA_OK;
+}
+
+u32 sa_phrase_stage_words() {
+    static const long env = getenv("SA_PHRASE_STAGE_WORDS") ? atol(getenv("SA_PHRASE_STAGE_WORDS")) : 0;
+    return env > 0 ? (u32)std::min<long>(env, 18 * 1024) : 8192u;
+}
+
+// Merge regime or search regime?  Staging reads every list once (8 * sum(W) bytes); the search path costs about
+// `ratio` bytes (a dozen 32-byte sectors of dependent probes) per driver element of the first step.
+bool sa_phrase_is_staged(const PhraseQuery &pq) {
+    static const long env = getenv("SA_PHRASE_STAGE_RATIO") ? atol(getenv("SA_PHRASE_STAGE_RATIO")) : -1;
+    const u64 ratio = env >= 0 ? (u64)env : 50;
+    if (ratio == 0) return false;
+    const u32 n = pq.n_terms;
+    if (n < 2) return false;
+    u64 sum = 0, drive = ~0ull;
+    for (u32 t = 0; t < n; t++) {
+        sum += pq.len[t];
+        if (pq.len[t] == 0) return false;
+    }
+    if (pq.mode == SA_PHRASE_MODE_LR) drive = std::min(pq.len[0], pq.len[1]);
+    else if (pq.mode == SA_PHRASE_MODE_RL) drive = std::min(pq.len[n - 1], pq.len[n - 2]);
+    else {
+        drive = std::min(pq.len[n - 1], pq.len[n - 2]);
+        if (pq.split >= 2) drive = std::max(drive, std::min(pq.len[0], pq.len[1]));
+    }
+    return drive * ratio > sum;
 }
 
 // ------------------------------------------------------------------------------- host side
@@ -576,7 +767,7 @@ static void step_order(const PhraseQuery &pq, std::vector<u32> &order) {
 // Runs phrase queries (already planned) into ix->dense; loops until the same-term speculation
 // of every query is confirmed.  lists may live in ix->d_words (off = absolute word offsets).
 int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
-                              int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump) {
+                              int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump, u64 staged_slab_cap) {
     const u32 Q = (u32)pqs.size();
     const u64 stride = padded(ix->n_docs);
     int rc;
@@ -598,20 +789,38 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         for (u32 t = 0; t < pq.n_terms; t++) sum += pq.len[t];
         arena_words += 6 * (sum + 2ull * n_chunks);
     }
+    // merge regime (single query on the index's own lists): persistent CTAs + TMA staging, no bump arena
+    const bool staged = staged_slab_cap && Q == 1 && d_words == ix->d_words && !dump.cont && sa_phrase_is_staged(pqs[0]);
+    if (staged) arena_words = 64;
     if ((rc = ix->phrase_scratch.reserve(arena_words * sizeof(u64) + 64))) return rc;
     unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
     u64 *d_arena = (u64 *)ix->phrase_scratch.p + 8;
     PhraseStats *d_stats = (PhraseStats *)ix->cand_meta.p;
     std::vector<PhraseStats> h_stats(Q);
     std::vector<u32> order;
+    if (staged) {
+        if ((rc = ix->misc.reserve(256))) return rc;
+        SA_CUDA(cudaMemsetAsync(ix->misc.p, 0, sizeof(u32), ix->stream));      // qsel = {0}
+    }
 
     for (int attempt = 0; attempt < (int)SA_MAX_PHRASE_TERMS + 2; attempt++) {
         SA_CUDA(cudaMemcpyAsync(ix->queries.p, pqs.data(), (size_t)Q * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
         SA_CUDA(cudaMemsetAsync(d_stats, 0, (size_t)Q * sizeof(PhraseStats), ix->stream));
         SA_CUDA(cudaMemsetAsync(d_used, 0, 64, ix->stream));
+        if (staged) {
+            PhraseSplit sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.d_staged = (const u32 *)ix->misc.p;
+            sp.n_staged = 1;
+            sp.staged_chunks = sa_phrase_staged_chunks(ix);
+            sp.slab_cap = staged_slab_cap;
+            if ((rc = sa_phrase_enqueue(ix, ix->queries.as<PhraseQuery>(), d_stats, 1, ix->dense.as<float>(), stride, 1, d_arena,
+                                        d_used, arena_words, score, p, nullptr, 0, &sp))) return rc;
+        } else {
         PhraseArgs a;      // (the kernel writes every tile of the dense rows itself: no zero-fill pass)
         memset(&a, 0, sizeof(a));
         a.words = d_words;
+        a.tile_dir = (d_words == ix->d_words) ? ix->d_tile_dir : nullptr;
         a.doc_lens = ix->d_doc_lens;
         a.n_docs = ix->n_docs;
         a.doc_base = ix->doc_base;
@@ -628,6 +837,7 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         a.score = score;
         a.dump = dump;
         if ((rc = launch_phrase(ix, a, Q))) return rc;
+        }
         SA_CUDA(cudaMemcpyAsync(h_stats.data(), d_stats, (size_t)Q * sizeof(PhraseStats), cudaMemcpyDeviceToHost, ix->stream));
         SA_CUDA(cudaStreamSynchronize(ix->stream));
         bool again = false;
@@ -689,10 +899,11 @@ static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks) {
 int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_stats, u32 Q,
                       float *dense_rows, u64 stride, u32 n_chunks, u64 *d_arena,
                       unsigned long long *d_arena_used, u64 arena_words, int score, const Bm25Params &p,
-                      const TopkCtx *topk, u32 topk_row0) {
+                      const TopkCtx *topk, u32 topk_row0, const PhraseSplit *split) {
     PhraseArgs a;
     memset(&a, 0, sizeof(a));
     a.words = ix->d_words;
+    a.tile_dir = ix->d_tile_dir;
     a.doc_lens = ix->d_doc_lens;
     a.n_docs = ix->n_docs;
     a.doc_base = ix->doc_base;
@@ -709,7 +920,52 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
     a.score = score;
     if (topk) a.topk = *topk;
     a.topk_row0 = topk_row0;
-    return launch_phrase(ix, a, Q);
+    if (!split || split->n_staged == 0) {
+        if (split) { a.qsel = split->d_search; a.n_sel = split->n_search; }
+        return launch_phrase(ix, a, split ? split->n_search : Q);
+    }
+    int rc;
+    if (split->n_search) {                      // search regime: one CTA per (query, chunk)
+        a.qsel = split->d_search;
+        a.n_sel = split->n_search;
+        if ((rc = launch_phrase(ix, a, split->n_search))) return rc;
+    }
+    // merge regime: persistent CTAs, TMA-staged segments
+    const u32 stage_words = sa_phrase_stage_words();
+    u32 ctas = 0;
+    if ((rc = staged_grid(ix, stage_words, &ctas))) return rc;
+    if ((rc = ix->phrase_slabs.reserve((size_t)ctas * 6 * split->slab_cap * sizeof(u64)))) return rc;
+    a.qsel = split->d_staged;
+    a.n_sel = split->n_staged;
+    a.n_chunks = split->staged_chunks;
+    a.docs_per_chunk = docs_per_chunk_of(ix, split->staged_chunks);
+    a.stage_words = stage_words;
+    a.slabs = ix->phrase_slabs.as<u64>();
+    a.slab_cap = split->slab_cap;
+    a.work_counter = (u32 *)(d_arena_used + 1);                 // zeroed with the arena counter
+    const u64 n_work = (u64)a.n_sel * a.n_chunks;
+    KernelTimer t(ix, 2);
+    phrase_staged_kernel<<<(unsigned)std::min<u64>(ctas, n_work), PT, (size_t)stage_words * sizeof(u64), ix->stream>>>(a);
+    SA_CUDA(cudaGetLastError());
+    t.stop();
+    ix->stats.phrase_kernel_launches++;
+    ix->stats.total_launches++;
+    return SA_OK;
+}
+
+// chunks of the merge regime: whole tiles, ~16 tiles each (segments are cut inside the kernel)
+u32 sa_phrase_staged_chunks(const sa_index *ix) {
+    const u64 n_tiles = (ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS;
+    return sa_phrase_chunks(ix, (u32)std::max<u64>(1, (n_tiles + 15) / 16));
+}
+
+// scratch entries per buffer a persistent CTA needs for this query: no segment slice is longer than the largest
+// per-tile slice of its terms (one-tile segments) or the staging capacity (multi-tile segments)
+u64 sa_phrase_slab_cap(const sa_index *ix, const u32 *term_ids, u32 n_terms) {
+    u64 cap = sa_phrase_stage_words();
+    for (u32 i = 0; i < n_terms; i++)
+        if (term_ids[i] != SA_NO_TERM && term_ids[i] < ix->n_terms) cap = std::max<u64>(cap, ix->h_max_tile_words[term_ids[i]]);
+    return cap + 8;
 }
 
 static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, uint32_t slop,
@@ -776,12 +1032,14 @@ static int phrase_common(sa_index *ix, const uint32_t *term_ids, uint32_t n_term
         for (u32 i = 0; i < n_terms; i++) {
             pq.off[i] = offs[i];
             pq.len[i] = lens[i];
+            if (d_lists == ix->d_words && ix->h_dir_off[term_ids[i]] != SA_NO_DIR) pq.dir_plus1[i] = ix->h_dir_off[term_ids[i]] + 1;
         }
         sa_phrase_plan(pq, term_ids);
         PhraseDump nodump;
         memset(&nodump, 0, sizeof(nodump));
         // raw counts first when BM25 must touch every doc
-        if ((rc = sa_phrase_run_sync(ix, pqs, d_lists, score && p.sparse_ok, p, 0, nodump))) return rc;
+        if ((rc = sa_phrase_run_sync(ix, pqs, d_lists, score && p.sparse_ok, p, 0, nodump,
+                                     d_lists == ix->d_words ? sa_phrase_slab_cap(ix, term_ids, n_terms) : 0))) return rc;
         raw_counts = score && !p.sparse_ok;
     } else {
         if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
@@ -852,7 +1110,7 @@ extern "C" int sa_op_bigram_freqs(const uint64_t *lhs, uint64_t n_lhs, const uin
             cudaMemsetAsync(dump.n_cont, 0, 2 * sizeof(u64), ix->stream);
             Bm25Params p;
             memset(&p, 0, sizeof(p));
-            rc = sa_phrase_run_sync(ix, pqs, ix->d_words, 0, p, 1, dump);
+            rc = sa_phrase_run_sync(ix, pqs, ix->d_words, 0, p, 1, dump, 0);
             if (!rc) {
                 u64 n[2];
                 cudaMemcpy(n, dump.n_cont, 2 * sizeof(u64), cudaMemcpyDeviceToHost);

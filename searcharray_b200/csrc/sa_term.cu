@@ -198,35 +198,64 @@ term_tile_kernel(const TermBatchArgs a) {
         //     lane takes FOUR records with one 16-byte load (record runs start 16-byte aligned; the slice is
         //     widened to whole quads and the strangers masked); no run detection, no shuffles, no popcount.
         const u32 *__restrict__ recs = a.recs + tq.rec_off;
-        for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
-            const u32 i = base + tid * 4;
-            uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
-            if (i < hi) r4 = __ldg(reinterpret_cast<const uint4 *>(recs + i));
-            const u32 rr[4] = {r4.x, r4.y, r4.z, r4.w};
-            float nr4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-            if (MODE == TERM_MODE_SCORE && !staged_norm) {
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (i + e >= lo && i + e < hi) nr4[e] = __ldg(norm + (rr[e] >> SA_REC_TF_BITS));
-            }
-            if (!norm_ready) {                             // CTA-uniform: first pass of a staged tile
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                __syncthreads();
-                norm_ready = true;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (i + e < lo || i + e >= hi) continue;
-                const u32 rel = rr[e] >> SA_REC_TF_BITS, tf = rr[e] & SA_REC_TF_MASK;
-                float v = (float)tf;
-                if (MODE == TERM_MODE_SCORE) {
-                    v = 0.0f;
-                    if (tf) {
-                        v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : nr4[e], tq.idf);
-                        my_max = max(my_max, __float_as_uint(v));
-                    }
+        if (hi - lo >= SA_TERM_THREADS * 4) {
+            for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
+                const u32 i = base + tid * 4;
+                uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+                if (i < hi) r4 = __ldg(reinterpret_cast<const uint4 *>(recs + i));
+                const u32 rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                float nr4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+                if (MODE == TERM_MODE_SCORE && !staged_norm) {
+    #pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (i + e >= lo && i + e < hi) nr4[e] = __ldg(norm + (rr[e] >> SA_REC_TF_BITS));
                 }
-                s_out[rel] = staged_norm ? -v : v;
+                if (!norm_ready) {                             // CTA-uniform: first pass of a staged tile
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncthreads();
+                    norm_ready = true;
+                }
+    #pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (i + e < lo || i + e >= hi) continue;
+                    const u32 rel = rr[e] >> SA_REC_TF_BITS, tf = rr[e] & SA_REC_TF_MASK;
+                    float v = (float)tf;
+                    if (MODE == TERM_MODE_SCORE) {
+                        v = 0.0f;
+                        if (tf) {
+                            v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : nr4[e], tq.idf);
+                            my_max = max(my_max, __float_as_uint(v));
+                        }
+                    }
+                    s_out[rel] = staged_norm ? -v : v;
+                }
+            }
+        } else {
+            // sparse tiles: ONE record per thread, so the threads' maxima (the tile bound of step 3) come from as
+            // many distinct docs as possible
+            for (u32 base = lo; base < hi; base += SA_TERM_THREADS) {                 // CTA-uniform trip count
+                const u32 i = base + tid;
+                const bool live = i < hi;
+                const u32 r = live ? __ldg(recs + i) : 0u;
+                float nrm = 1.0f;
+                if (MODE == TERM_MODE_SCORE && !staged_norm && live) nrm = __ldg(norm + (r >> SA_REC_TF_BITS));
+                if (!norm_ready) {                         // CTA-uniform: first pass of a staged tile
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncthreads();
+                    norm_ready = true;
+                }
+                if (live) {
+                    const u32 rel = r >> SA_REC_TF_BITS, tf = r & SA_REC_TF_MASK;
+                    float v = (float)tf;
+                    if (MODE == TERM_MODE_SCORE) {
+                        v = 0.0f;
+                        if (tf) {
+                            v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : nrm, tq.idf);
+                            my_max = max(my_max, __float_as_uint(v));
+                        }
+                    }
+                    s_out[rel] = staged_norm ? -v : v;
+                }
             }
         }
     } else {
