@@ -64,6 +64,11 @@ int sa_index_create(const uint64_t *words, uint64_t n_words,
                     const float *doc_lens, uint64_t n_docs, uint64_t doc_base,
                     int device, sa_index **index_out);
 int sa_index_destroy(sa_index *index);
+/* How sa_index_create moved the posting words to HBM: 0 = plain copy (small indexes), 1 = the host
+ * range -- e.g. the np.memmap of the reference's MemoryMappedArrays .dat file (phrase/memmap_arrays.py:145-208) --
+ * was page-locked in place with cudaHostRegister and DMA'd at PCIe rate, 2 = pipelined through pinned bounce
+ * buffers because the range could not be registered. */
+int sa_index_upload_mode(const sa_index *index, int *mode_out);
 int sa_index_info(const sa_index *index, uint64_t *n_docs, uint64_t *n_words,
                   uint32_t *n_terms, uint64_t *device_bytes);
 

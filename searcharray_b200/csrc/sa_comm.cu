@@ -121,16 +121,16 @@ extern "C" int sa_comm_allreduce_max(sa_index *ix, double *inout) {
     return SA_OK;
 }
 
-// enqueue: all-gather the per-shard result keys and merge (async on the library stream)
+// enqueue: all-gather the per-shard result blocks (keys + summary tail) and merge (async on the library stream)
 static int enqueue_allgather_merge(sa_index *ix, size_t nq, u32 k) {
-    const size_t nk = nq * k;
-    if (nk == 0) return SA_OK;
+    const size_t nk = nq * k, blk = nk + SA_BATCH_TAIL;
     int rc;
-    if ((rc = ix->gather.reserve(((size_t)ix->world + 1) * nk * sizeof(u64)))) return rc;
+    if ((rc = ix->gather.reserve(((size_t)ix->world * blk + nk + 8) * sizeof(u64)))) return rc;
     u64 *d_all = ix->gather.as<u64>();
-    u64 *d_merged = d_all + (size_t)ix->world * nk;
-    SA_NCCL(ncclAllGather(ix->topk_out.p, d_all, nk, ncclUint64, (ncclComm_t)ix->nccl_comm, ix->stream));
-    return launch_topk_merge(ix, d_all, (u32)ix->world, (u32)nq, k, d_merged);
+    u64 *d_merged = d_all + (size_t)ix->world * blk;
+    SA_NCCL(ncclAllGather(ix->topk_out.p, d_all, blk, ncclUint64, (ncclComm_t)ix->nccl_comm, ix->stream));
+    if (nk == 0) return SA_OK;
+    return launch_topk_merge(ix, d_all, blk, (u32)ix->world, (u32)nq, k, d_merged);
 }
 
 extern "C" int sa_batch_execute_allgather(sa_index *ix) {
@@ -143,32 +143,48 @@ extern "C" int sa_batch_execute_allgather(sa_index *ix) {
     return enqueue_allgather_merge(ix, nq, k);
 }
 
+// merged keys + every rank's summary tail in one synchronise
+static int download_merged(sa_index *ix, size_t nq, u32 k, uint32_t *out_docs, float *out_scores, u64 *redo_all, u64 *redo_mine,
+                           bool count_stats) {
+    const size_t nk = nq * k, blk = nk + SA_BATCH_TAIL;
+    int rc;
+    if ((rc = sa_pinned_reserve(ix, (nk + (size_t)ix->world * SA_BATCH_TAIL) * sizeof(u64)))) return rc;
+    u64 *h = (u64 *)ix->h_pinned;
+    const u64 *d_all = ix->gather.as<u64>();
+    const u64 *d_merged = d_all + (size_t)ix->world * blk;
+    if (nk) SA_CUDA(cudaMemcpyAsync(h, d_merged, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaMemcpy2DAsync(h + nk, SA_BATCH_TAIL * sizeof(u64), d_all + nk, blk * sizeof(u64), SA_BATCH_TAIL * sizeof(u64),
+                              (size_t)ix->world, cudaMemcpyDeviceToHost, ix->stream));
+    SA_CUDA(cudaStreamSynchronize(ix->stream));
+    sa_unpack_keys(h, nk, out_docs, out_scores);
+    *redo_all = 0;
+    for (int r = 0; r < ix->world; r++) *redo_all += h[nk + (size_t)r * SA_BATCH_TAIL];
+    *redo_mine = h[nk + (size_t)ix->rank * SA_BATCH_TAIL];
+    if (count_stats) {
+        ix->stats.phrase_cont_words += h[nk + (size_t)ix->rank * SA_BATCH_TAIL + 1];
+        ix->stats.phrase_matched_docs += h[nk + (size_t)ix->rank * SA_BATCH_TAIL + 2];
+    }
+    return SA_OK;
+}
+
 extern "C" int sa_batch_download_allgather(sa_index *ix, uint32_t *out_docs, float *out_scores,
                                            uint32_t *n_overflow) {
     SA_CHECK(ix && ix->nccl_comm && out_docs && out_scores, "NULL argument / no communicator");
     std::lock_guard<std::mutex> g(ix->mu);
     u32 nq, k, redone = 0;
     sa_batch_dims(ix, &nq, &k);
-    int rc = sa_batch_fix_overflow_locked(ix, &redone);
-    if (rc) return rc;
+    if (n_overflow) *n_overflow = 0;
+    // every rank sees every rank's "queries to re-run" count (it travelled with the all-gathered keys), so all ranks
+    // take the same path without a separate collective
+    u64 redo_all = 0, redo_mine = 0;
+    int rc = download_merged(ix, nq, k, out_docs, out_scores, &redo_all, &redo_mine, true);
+    if (rc || redo_all == 0) return rc;
+    if (redo_mine && (rc = sa_batch_fix_overflow_locked(ix, &redone))) return rc;
     if (n_overflow) *n_overflow = redone;
-    // every rank must take the same path: agree on "somebody re-ran a query"
-    int rc2 = ix->misc.reserve(256);
-    if (rc2) return rc2;
-    float flag = redone ? 1.0f : 0.0f;
-    SA_CUDA(cudaMemcpyAsync(ix->misc.p, &flag, sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-    SA_NCCL(ncclAllReduce(ix->misc.p, ix->misc.p, 1, ncclFloat, ncclMax, (ncclComm_t)ix->nccl_comm, ix->stream));
-    SA_CUDA(cudaMemcpyAsync(&flag, ix->misc.p, sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-    SA_CUDA(cudaStreamSynchronize(ix->stream));
-    if (flag != 0.0f && (rc = enqueue_allgather_merge(ix, nq, k))) return rc;
-    const size_t nk = (size_t)nq * k;
-    if (nk == 0) return SA_OK;
-    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
-    const u64 *d_merged = ix->gather.as<u64>() + (size_t)ix->world * nk;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_merged, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
-    SA_CUDA(cudaStreamSynchronize(ix->stream));
-    sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
-    return SA_OK;
+    // the repaired keys sit in topk_out; clear this rank's tail so the second gather reports a clean batch
+    SA_CUDA(cudaMemsetAsync(ix->topk_out.as<u64>() + (size_t)nq * k, 0, SA_BATCH_TAIL * sizeof(u64), ix->stream));
+    if ((rc = enqueue_allgather_merge(ix, nq, k))) return rc;
+    return download_merged(ix, nq, k, out_docs, out_scores, &redo_all, &redo_mine, false);
 }
 
 extern "C" int sa_score_batch_topk_allgather(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,

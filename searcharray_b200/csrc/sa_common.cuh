@@ -110,6 +110,7 @@ struct sa_index {
     u64 n_docs = 0, n_words = 0, doc_base = 0;
     u32 n_terms = 0;
     bool doc_lens_nonneg = true;
+    int upload_mode = 0;             // how the posting words reached HBM (sa_index_upload_mode)
 
     // HBM-resident index
     u64 *d_words = nullptr;          // [n_words + 1] (one readable pad word)

@@ -49,6 +49,60 @@ int sa_pinned_reserve(sa_index *ix, size_t bytes) {
     return SA_OK;
 }
 
+// --------------------------------------------------------------- bulk upload
+// the posting words usually sit in pageable memory -- a numpy array, or the np.memmap of the
+// reference's MemoryMappedArrays `.dat` file (phrase/memmap_arrays.py:145-208).  A plain cudaMemcpy from pageable
+// memory crawls through the driver's small staging buffers; instead the source range is page-locked IN PLACE
+// (cudaHostRegister, read-only: works on a read-only file mapping too) and copied by DMA at PCIe rate straight from
+// the page cache / the array.  If the range cannot be registered (old kernels, exotic mappings) the copy is pipelined
+// through two pinned bounce buffers.  mode_out: 0 plain copy (small), 1 registered in place, 2 pinned bounce.
+static int upload_bulk(void *dst, const void *src, size_t bytes, cudaStream_t stream, int *mode_out) {
+    *mode_out = 0;
+    if (bytes == 0) return SA_OK;
+    static const bool no_register = getenv("SA_NO_HOST_REGISTER") && atoi(getenv("SA_NO_HOST_REGISTER")) != 0;
+    if (bytes >= (32u << 20)) {
+        if (!no_register && cudaHostRegister((void *)src, bytes, cudaHostRegisterReadOnly) == cudaSuccess) {
+            cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            cudaHostUnregister((void *)src);
+            if (e != cudaSuccess) { sa_set_error("registered upload failed: %s", cudaGetErrorString(e)); return SA_ERR_CUDA; }
+            *mode_out = 1;
+            return SA_OK;
+        }
+        cudaGetLastError();                                   // registration refused: clear the error, bounce instead
+        const size_t CH = 32u << 20;
+        void *pin[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool ok = cudaHostAlloc(&pin[0], CH, cudaHostAllocDefault) == cudaSuccess &&
+                  cudaHostAlloc(&pin[1], CH, cudaHostAllocDefault) == cudaSuccess &&
+                  cudaEventCreate(&ev[0]) == cudaSuccess && cudaEventCreate(&ev[1]) == cudaSuccess;
+        if (ok) {
+            size_t at = 0;
+            int b = 0;
+            cudaError_t e = cudaSuccess;
+            while (at < bytes && e == cudaSuccess) {
+                const size_t n = std::min(CH, bytes - at);
+                e = cudaEventSynchronize(ev[b]);              // the previous copy out of this buffer is done
+                if (e != cudaSuccess) break;
+                memcpy(pin[b], (const char *)src + at, n);
+                e = cudaMemcpyAsync((char *)dst + at, pin[b], n, cudaMemcpyHostToDevice, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[b], stream);
+                at += n;
+                b ^= 1;
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            for (int i = 0; i < 2; i++) { cudaFreeHost(pin[i]); cudaEventDestroy(ev[i]); }
+            if (e != cudaSuccess) { sa_set_error("bounce upload failed: %s", cudaGetErrorString(e)); return SA_ERR_CUDA; }
+            *mode_out = 2;
+            return SA_OK;
+        }
+        for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+        cudaGetLastError();
+    }
+    SA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return SA_OK;
+}
+
 // --------------------------------------------------------------- df at upload
 // docfreq = number of distinct doc ids among a term's words (reference: unique(words >> 36)
 // .size, roaringish/unique.pyx:87-104 via middle_out.py:521-528).  One thread per word; a word
@@ -281,8 +335,10 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
     CREATE_CUDA(cudaEventCreate(&ix->ev1));
     CREATE_CUDA(cudaMalloc(&ix->d_words, (n_words + 4) * sizeof(u64)));
     CREATE_CUDA(cudaMemsetAsync(ix->d_words + n_words, 0, 4 * sizeof(u64), ix->stream));
-    if (n_words)
-        CREATE_CUDA(cudaMemcpyAsync(ix->d_words, words, n_words * sizeof(u64), cudaMemcpyHostToDevice, ix->stream));
+    if (n_words && upload_bulk(ix->d_words, words, n_words * sizeof(u64), ix->stream, &ix->upload_mode) != SA_OK) {
+        sa_index_destroy(ix);
+        return SA_ERR_CUDA;
+    }
     CREATE_CUDA(cudaMalloc(&ix->d_doc_lens, (n_docs + 1) * sizeof(float)));
     if (n_docs)
         CREATE_CUDA(cudaMemcpyAsync(ix->d_doc_lens, doc_lens, n_docs * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
@@ -482,6 +538,12 @@ extern "C" int sa_index_info(const sa_index *ix, uint64_t *n_docs, uint64_t *n_w
     return SA_OK;
 }
 
+extern "C" int sa_index_upload_mode(const sa_index *ix, int *mode_out) {
+    SA_CHECK(ix && mode_out, "NULL argument");
+    *mode_out = ix->upload_mode;
+    return SA_OK;
+}
+
 extern "C" int sa_docfreq(sa_index *ix, uint32_t term_id, uint64_t *df_out) {
     SA_CHECK(ix && df_out, "NULL argument");
     if (term_id == SA_NO_TERM) { *df_out = 0; return SA_OK; }
@@ -649,6 +711,7 @@ struct BatchState {
     DevBuf d_pstats;                          // PhraseStats[#phrase queries]
     std::vector<u32> sel;                     // per chunk: search-regime then merge-regime phrase indices
     DevBuf d_sel;
+    DevBuf d_missing;                         // phrase_missing on the device (batch_summary_kernel)
 };
 
 static TermQuery make_term_query(const sa_index *ix, u32 t, float idf) {
@@ -723,7 +786,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     B.tqs.clear(); B.pqs.clear(); B.row_query.clear(); B.term_query.clear(); B.phrase_query.clear();
     B.phrase_missing.clear(); B.chunks.clear(); B.sel.clear();
     int rc;
-    if ((rc = ix->topk_out.reserve(std::max<size_t>((size_t)n_queries * k * sizeof(u64), 256)))) return rc;
+    if ((rc = ix->topk_out.reserve(std::max<size_t>(((size_t)n_queries * k + SA_BATCH_TAIL) * sizeof(u64), 256)))) return rc;
     if (n_queries == 0) { B.ready = true; return SA_OK; }
     const u64 stride = padded_docs(std::max<u64>(ix->n_docs, 1));
     // chunk so the dense score vectors of one chunk stay within ~4 GB of HBM
@@ -829,6 +892,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     if ((rc = B.d_meta.reserve((size_t)n_queries * sizeof(u32)))) return rc;
     if ((rc = B.d_pstats.reserve(std::max<size_t>(B.pqs.size() * sizeof(PhraseStats), 64)))) return rc;
     if ((rc = B.d_sel.reserve(std::max<size_t>(B.sel.size() * sizeof(u32), 64)))) return rc;
+    if ((rc = B.d_missing.reserve(std::max<size_t>(B.phrase_missing.size() * sizeof(u32), 64)))) return rc;
     if (!B.pqs.empty() && (rc = ix->phrase_scratch.reserve(max_arena * sizeof(u64) + 64))) return rc;
     if (n_span) {
         if ((rc = ix->phrase_scratch.reserve(max_span_scratch))) return rc;
@@ -850,10 +914,53 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
     if (!B.pqs.empty()) {
         SA_CUDA(cudaMemcpyAsync(B.d_pq.p, B.pqs.data(), B.pqs.size() * sizeof(PhraseQuery), cudaMemcpyHostToDevice, ix->stream));
         SA_CUDA(cudaMemcpyAsync(B.d_sel.p, B.sel.data(), B.sel.size() * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+        SA_CUDA(cudaMemcpyAsync(B.d_missing.p, B.phrase_missing.data(), B.phrase_missing.size() * sizeof(u32),
+                                cudaMemcpyHostToDevice, ix->stream));
     }
     SA_CUDA(cudaMemcpyAsync(B.d_row_query.p, B.row_query.data(), (size_t)n_queries * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
     B.ready = true;
     return SA_OK;
+}
+
+// Last kernel of a batch: how many queries need the exact re-run, and the phrase roofline counters.  The same-term
+// speculation of every phrase query is verified here exactly as sa_phrase_guess_ok does on the host.
+__global__ void __launch_bounds__(256)
+batch_summary_kernel(const u32 *__restrict__ ovf, u32 nq, const PhraseQuery *__restrict__ pqs,
+                     const PhraseStats *__restrict__ st, const u32 *__restrict__ missing, u32 n_phrase,
+                     u64 *__restrict__ tail) {
+    __shared__ unsigned long long s_acc[3];
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long redo = 0, cont = 0, match = 0;
+    for (u32 i = threadIdx.x; i < nq; i += blockDim.x) redo += ovf[i] ? 1 : 0;
+    for (u32 i = threadIdx.x; i < n_phrase; i += blockDim.x) {
+        const PhraseQuery &pq = pqs[i];
+        const PhraseStats &s = st[i];
+        cont += s.n_cont;
+        match += s.n_match;
+        bool bad = s.overflow != 0;
+        if (!bad && !missing[i]) {
+            const u32 n = pq.n_terms;
+            // every step the plan runs (sa_phrase.cu step_order): LR 1..n-1, RL 0..n-2, middle-out 1..split-1 and split..n-2
+            u32 s0 = 1, s1 = n;
+            if (pq.mode == SA_PHRASE_MODE_RL) { s0 = 0; s1 = n - 1; }
+            else if (pq.mode == SA_PHRASE_MODE_MID) { s0 = 1; s1 = n - 1; }
+            for (u32 step = s0; step < s1 && !bad; step++) {
+                const bool actual = s.n_inner[step] > 0 && s.n_diff[step] == 0;
+                const bool guess = (pq.same_guess >> step) & 1u;
+                if (actual != guess) bad = true;
+            }
+        }
+        // a wrong guess also sets the query's overflow flag?  No: the host re-derives which queries to redo; here
+        // only the COUNT matters (non-zero -> the host takes the slow path)
+        if (bad) redo++;
+    }
+    if (redo) atomicAdd(&s_acc[0], redo);
+    if (cont) atomicAdd(&s_acc[1], cont);
+    if (match) atomicAdd(&s_acc[2], match);
+    __syncthreads();
+    if (threadIdx.x < 3) tail[threadIdx.x] = s_acc[threadIdx.x];
+    if (threadIdx.x == 3) tail[3] = 0;
 }
 
 int sa_batch_execute_locked(sa_index *ix) {
@@ -861,9 +968,12 @@ int sa_batch_execute_locked(sa_index *ix) {
     BatchState &B = *ix->batch;
     SA_CUDA(cudaSetDevice(ix->device));
     u64 *d_keys = ix->topk_out.as<u64>();
-    if (B.nq == 0) return SA_OK;
+    if (B.nq == 0) {
+        SA_CUDA(cudaMemsetAsync(d_keys, 0, SA_BATCH_TAIL * sizeof(u64), ix->stream));
+        return SA_OK;
+    }
     if (ix->n_docs == 0 || B.avg_doc_len == 0.0f) {
-        SA_CUDA(cudaMemsetAsync(d_keys, 0, (size_t)B.nq * B.k * sizeof(u64), ix->stream));
+        SA_CUDA(cudaMemsetAsync(d_keys, 0, ((size_t)B.nq * B.k + SA_BATCH_TAIL) * sizeof(u64), ix->stream));
         return SA_OK;
     }
     const u64 stride = padded_docs(ix->n_docs);
@@ -908,6 +1018,11 @@ int sa_batch_execute_locked(sa_index *ix) {
         }
         if ((rc = launch_topk_select(ix, t, Q, ix->doc_base, d_keys, B.d_row_query.as<u32>() + C.row0))) return rc;
     }
+    const u32 n_phr = B.slop > 0 ? 0u : (u32)B.pqs.size();
+    batch_summary_kernel<<<1, 256, 0, ix->stream>>>(d_ovf, B.nq, B.d_pq.as<PhraseQuery>(), B.d_pstats.as<PhraseStats>(),
+                                                   B.d_missing.as<u32>(), n_phr, d_keys + (size_t)B.nq * B.k);
+    SA_CUDA(cudaGetLastError());
+    ix->stats.total_launches++;
     return SA_OK;
 }
 
@@ -958,10 +1073,7 @@ int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
     std::vector<u32> ovf((const u32 *)ix->h_pinned, (const u32 *)ix->h_pinned + B.nq);       // row space
     std::vector<PhraseStats> st(B.pqs.size());
     if (st_bytes) memcpy(st.data(), (char *)ix->h_pinned + ovf_bytes, st_bytes);
-    for (const PhraseStats &s : st) {
-        ix->stats.phrase_cont_words += s.n_cont;
-        ix->stats.phrase_matched_docs += s.n_match;
-    }
+
     struct Redo { bool phrase; u32 idx, q; const SpanQuery *sq; };
     std::vector<Redo> redo;
     size_t chunk_i = 0;
@@ -1012,14 +1124,29 @@ void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_score
     }
 }
 
-static int download_keys(sa_index *ix, const u64 *d_keys, size_t nk, uint32_t *out_docs, float *out_scores) {
-    if (nk == 0) return SA_OK;
+// keys + the batch's summary tail in ONE device-to-host copy and ONE synchronise
+static int download_keys(sa_index *ix, const u64 *d_keys, size_t nk, uint32_t *out_docs, float *out_scores, u64 *tail) {
     int rc;
-    if ((rc = sa_pinned_reserve(ix, nk * sizeof(u64)))) return rc;
-    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_keys, nk * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
+    if ((rc = sa_pinned_reserve(ix, (nk + SA_BATCH_TAIL) * sizeof(u64)))) return rc;
+    SA_CUDA(cudaMemcpyAsync(ix->h_pinned, d_keys, (nk + SA_BATCH_TAIL) * sizeof(u64), cudaMemcpyDeviceToHost, ix->stream));
     SA_CUDA(cudaStreamSynchronize(ix->stream));
     sa_unpack_keys((const u64 *)ix->h_pinned, nk, out_docs, out_scores);
+    if (tail) memcpy(tail, (const u64 *)ix->h_pinned + nk, SA_BATCH_TAIL * sizeof(u64));
     return SA_OK;
+}
+
+int sa_batch_download_locked(sa_index *ix, uint32_t *out_docs, float *out_scores, uint32_t *n_overflow) {
+    BatchState &B = *ix->batch;
+    const size_t nk = (size_t)B.nq * B.k;
+    u64 tail[SA_BATCH_TAIL] = {0, 0, 0, 0};
+    if (n_overflow) *n_overflow = 0;
+    int rc = download_keys(ix, ix->topk_out.as<u64>(), nk, out_docs, out_scores, tail);
+    if (rc) return rc;
+    ix->stats.phrase_cont_words += tail[1];
+    ix->stats.phrase_matched_docs += tail[2];
+    if (tail[0] == 0) return SA_OK;              // the common case: nothing to repair
+    if ((rc = sa_batch_fix_overflow_locked(ix, n_overflow))) return rc;
+    return download_keys(ix, ix->topk_out.as<u64>(), nk, out_docs, out_scores, nullptr);
 }
 
 extern "C" int sa_batch_upload(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
@@ -1040,9 +1167,7 @@ extern "C" int sa_batch_download(sa_index *ix, uint32_t *out_docs, float *out_sc
     SA_CHECK(ix && ix->batch && ix->batch->ready, "no batch uploaded");
     SA_CHECK(out_docs && out_scores, "NULL argument");
     std::lock_guard<std::mutex> g(ix->mu);
-    int rc = sa_batch_fix_overflow_locked(ix, n_overflow);
-    if (rc) return rc;
-    return download_keys(ix, ix->topk_out.as<u64>(), (size_t)ix->batch->nq * ix->batch->k, out_docs, out_scores);
+    return sa_batch_download_locked(ix, out_docs, out_scores, n_overflow);
 }
 
 extern "C" int sa_score_batch_topk(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
@@ -1054,8 +1179,7 @@ extern "C" int sa_score_batch_topk(sa_index *ix, const uint32_t *terms, const ui
     int rc = sa_batch_upload_locked(ix, terms, term_starts, idf, n_queries, slop, avg_doc_len, k1, b, k);
     if (rc) return rc;
     if ((rc = sa_batch_execute_locked(ix))) return rc;
-    if ((rc = sa_batch_fix_overflow_locked(ix, nullptr))) return rc;
-    return download_keys(ix, ix->topk_out.as<u64>(), (size_t)n_queries * k, out_docs, out_scores);
+    return sa_batch_download_locked(ix, out_docs, out_scores, nullptr);
 }
 
 // ------------------------------------------------------------------- timers
@@ -1126,6 +1250,7 @@ void sa_free_batch(sa_index *ix) {
     ix->batch->d_meta.release();
     ix->batch->d_pstats.release();
     ix->batch->d_sel.release();
+    ix->batch->d_missing.release();
     ix->batch->d_sq.release();
     ix->batch->d_scounts.release();
     ix->batch->d_sidf.release();

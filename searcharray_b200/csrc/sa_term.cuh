@@ -55,7 +55,13 @@ TermQuery sa_make_term_query(const sa_index *ix, u32 term_id, float idf);
 // place on the way (row_idf[i] = idf of row row0 + i)
 int launch_dense_topk_tiles(sa_index *ix, float *dense, u64 stride, u32 row0, u32 n_rows, const TopkCtx &t,
                             const float *d_row_idf);
-int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out);
+int launch_topk_merge(sa_index *ix, const u64 *d_in, u64 rank_stride, u32 world, u32 n_queries, u32 k, u64 *d_out);
+// A batch's result block in HBM: nq * k keys followed by SA_BATCH_TAIL summary words written by the batch's last
+// kernel -- [0] queries that need the exact host-side re-run (candidate overflow, wrong same-term guess, scratch
+// exhausted), [1] continuation words and [2] matched docs of the phrase queries (roofline accounting).  The tail
+// travels with the keys (one D2H; one all-gather when sharded), so a clean batch costs ONE stream synchronise.
+#define SA_BATCH_TAIL 4
+int sa_batch_download_locked(sa_index *ix, uint32_t *out_docs, float *out_scores, uint32_t *n_overflow);
 // batch plumbing shared by sa_index.cu / sa_comm.cu (callers hold ix->mu)
 int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *term_starts,
                            const float *idf, uint32_t n_queries, uint32_t slop,

@@ -176,7 +176,7 @@ topk_select_kernel(TopkCtx t, u64 doc_base, u64 *__restrict__ out_keys, const u3
 
 // Merge per-shard top-k lists after the all-gather: in[r][q][k] -> out[q][k].
 __global__ void __launch_bounds__(SEL_THREADS)
-topk_merge_kernel(const u64 *__restrict__ in, u32 world, u32 n_queries, u32 k, u64 *__restrict__ out) {
+topk_merge_kernel(const u64 *__restrict__ in, u64 rank_stride, u32 world, u32 n_queries, u32 k, u64 *__restrict__ out) {
     __shared__ u64 s_keys[SEL_SMEM_KEYS];
     const u32 q = blockIdx.x;
     const u32 n = world * k;
@@ -186,7 +186,7 @@ topk_merge_kernel(const u64 *__restrict__ in, u32 world, u32 n_queries, u32 k, u
         u64 v = 0ull;
         if (i < n) {
             u32 r = i / k, j = i % k;
-            v = in[((u64)r * n_queries + q) * k + j];
+            v = in[(u64)r * rank_stride + (u64)q * k + j];
         }
         s_keys[i] = v;
     }
@@ -207,11 +207,11 @@ int launch_topk_select(sa_index *ix, const TopkCtx &t, u32 n_queries, u64 doc_ba
     return SA_OK;
 }
 
-int launch_topk_merge(sa_index *ix, const u64 *d_in, u32 world, u32 n_queries, u32 k, u64 *d_out) {
+int launch_topk_merge(sa_index *ix, const u64 *d_in, u64 rank_stride, u32 world, u32 n_queries, u32 k, u64 *d_out) {
     if (n_queries == 0) return SA_OK;
     SA_CHECK((u64)world * k <= SEL_SMEM_KEYS, "world*k too large for the merge kernel");
     KernelTimer tm(ix, 1);
-    topk_merge_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(d_in, world, n_queries, k, d_out);
+    topk_merge_kernel<<<n_queries, SEL_THREADS, 0, ix->stream>>>(d_in, rank_stride, world, n_queries, k, d_out);
     SA_CUDA(cudaGetLastError());
     tm.stop();
     ix->stats.topk_kernel_launches++;

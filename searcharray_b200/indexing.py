@@ -52,6 +52,7 @@ class HostIndex:
 
     def __init__(self, words, term_offsets, term_lengths, doc_lens, term_dict=None, avg_doc_length=None):
         self.words = np.ascontiguousarray(words, dtype=np.uint64)
+        self.words_file = None
         self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
         self.term_lengths = np.ascontiguousarray(term_lengths, dtype=np.uint64)
         self.doc_lens = np.ascontiguousarray(doc_lens, dtype=np.float32)
@@ -60,6 +61,34 @@ class HostIndex:
         if avg_doc_length is None:
             avg_doc_length = np.mean(self.doc_lens) if len(self.doc_lens) else 0
         self.avg_doc_length = avg_doc_length
+
+    # ---- on-disk posting words (reference phrase/memmap_arrays.py:145-208, MemoryMappedArrays): the words
+    #      array written once to `<data_dir>/<n>.dat`, mapped back read-only; pickling stores the file name
+    #      and the per-term slices, not the words (reference :196-208)
+    def memmap(self, data_dir):
+        import os
+        os.makedirs(data_dir, exist_ok=True)
+        filename = os.path.join(data_dir, f"{len(os.listdir(data_dir))}.dat")     # create_filename, :8-13
+        with open(filename, "wb") as f:
+            self.words.tofile(f)
+        self.words_file = filename
+        self._map_words()
+        return filename
+
+    def _map_words(self):
+        n = int(np.sum(self.term_lengths))
+        self.words = np.memmap(self.words_file, dtype=np.uint64, mode="r", shape=(n,)) if n else np.empty(0, dtype=np.uint64)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if st.get("words_file"):
+            st["words"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        if st.get("words_file"):
+            self._map_words()
 
     @property
     def n_terms(self):

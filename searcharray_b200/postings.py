@@ -151,8 +151,10 @@ class DeviceIndex:
         self.handle = ctypes.c_void_p()
         self.n_docs = host.n_docs
         self._rows_set = False
+        words = host.words
+        words_ptr = ctypes.cast(words.ctypes.data, _lib.P_u64) if len(words) else None   # (also a read-only memmap)
         _lib.check(_lib.lib().sa_index_create(
-            _lib.p_u64(host.words), len(host.words), _lib.p_u64(host.term_offsets),
+            words_ptr, len(words), _lib.p_u64(host.term_offsets),
             _lib.p_u64(host.term_lengths), host.n_terms, _lib.p_f32(host.doc_lens), host.n_docs,
             doc_base, device, ctypes.byref(self.handle)))
         self._finalizer = weakref.finalize(self, DeviceIndex._destroy, self.handle)
@@ -215,10 +217,14 @@ class SearchArray(ExtensionArray):
               device=0) -> "SearchArray":
         """Index an array of strings (reference postings.py:249-300).  batch_size / workers /
         cache_gt_than / data_dir / autowarm are accepted for signature compatibility: the
-        per-term df table the reference warms lazily is computed on the device at upload."""
+        per-term df table the reference warms lazily is computed on the device at upload.  data_dir:
+        the posting words are written to `<data_dir>/<n>.dat` and memory-mapped (reference MemoryMappedArrays); the
+        upload then DMAs straight from the mapping (cudaHostRegister), and a pickle carries the file name only."""
         if not is_list_like(array):
             raise TypeError("Expected list-like object, got {}".format(type(array)))
         host = build_index(list(array), tokenizer, truncate=truncate)
+        if data_dir is not None:            # reference indexing.py:228-230, 291-293: memmap the bit positions
+            host.memmap(data_dir)
         return cls.from_host_index(host, tokenizer=tokenizer, avoid_copies=avoid_copies, device=device)
 
     @classmethod
