@@ -286,6 +286,15 @@ int sa_op_payload_slice(const uint64_t *arr, uint64_t n, uint64_t msb_mask, uint
 int sa_op_as_dense(const uint64_t *indices, const float *values, uint64_t n, uint64_t size, int device, float *out);
 uint64_t sa_op_last_staged_ctas(void);
 
+/* ------------------------------------------------------------ index build (8f-4)
+ * The numpy half of the reference's index build after tokenisation (searcharray/indexing.py:101-145:
+ * stable sort of the (term, doc, posn) triples by term; searcharray/roaringish/roaringish.py:93-142: encode) on
+ * the device.  Triples in document order as _gather_tokens emits them (indexing.py:64-98); term ids < n_terms.
+ * words_out: room for n_triples words; term_off_out / term_len_out: every term's slice of words_out. */
+int sa_op_build_index(const uint32_t *term_ids, const uint32_t *doc_ids, const uint32_t *posns, uint64_t n_triples,
+                      uint32_t n_terms, int device, uint64_t *words_out, uint64_t *n_words_out,
+                      uint64_t *term_off_out, uint64_t *term_len_out);
+
 #ifdef __cplusplus
 }
 #endif

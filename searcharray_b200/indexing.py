@@ -120,9 +120,11 @@ class HostIndex:
         return HostIndex(words, offs, lens, self.doc_lens[doc_lo:doc_hi], self.term_dict, self.avg_doc_length)
 
 
-def build_index(array, tokenizer, truncate=False):
+def build_index(array, tokenizer, truncate=False, gpu_build=None):
     """Strings -> HostIndex (reference indexing.py:64-145,235-295 semantics: term ids in
-    first-seen order, position = token index, doc_len = number of tokens)."""
+    first-seen order, position = token index, doc_len = number of tokens).  Tokenising is a Python loop
+    and stays on the host; with `gpu_build=<device>` the sort + roaringish encode of the (term, doc, posn)
+    triples runs on that GPU (sa_op_build_index), otherwise in numpy."""
     term_dict = TermDict()
     all_terms, all_docs, all_posns = [], [], []
     doc_lens = np.zeros(len(array), dtype=np.float32)
@@ -143,6 +145,8 @@ def build_index(array, tokenizer, truncate=False):
         terms = np.concatenate(all_terms)
         docs = np.concatenate(all_docs)
         posns = np.concatenate(all_posns)
+        if gpu_build is not None:
+            return _build_on_device(terms, docs, posns, n_terms, doc_lens, term_dict, gpu_build)
         order = np.argsort(terms, kind="stable")       # docs/posns already ascending
         words, uniq, offs, lens = encode_grouped(terms[order], docs[order], posns[order])
     else:
@@ -154,6 +158,22 @@ def build_index(array, tokenizer, truncate=False):
     term_offsets[uniq] = offs
     term_lengths[uniq] = lens
     return HostIndex(words, term_offsets, term_lengths, doc_lens, term_dict)
+
+
+def _build_on_device(terms, docs, posns, n_terms, doc_lens, term_dict, device):
+    import ctypes
+    from . import _lib
+    t32 = np.ascontiguousarray(terms, dtype=np.uint32)
+    d32 = np.ascontiguousarray(docs, dtype=np.uint32)
+    p32 = np.ascontiguousarray(posns, dtype=np.uint32)
+    words = np.empty(len(t32), dtype=np.uint64)
+    offs = np.zeros(n_terms, dtype=np.uint64)
+    lens = np.zeros(n_terms, dtype=np.uint64)
+    n_words = ctypes.c_uint64(0)
+    _lib.check(_lib.lib().sa_op_build_index(_lib.p_u32(t32), _lib.p_u32(d32), _lib.p_u32(p32), len(t32), n_terms,
+                                            int(device), _lib.p_u64(words), ctypes.byref(n_words),
+                                            _lib.p_u64(offs), _lib.p_u64(lens)))
+    return HostIndex(words[:n_words.value].copy(), offs, lens, doc_lens, term_dict)
 
 
 def index_from_term_postings(term_names, term_words_list, doc_lens, avg_doc_length=None):

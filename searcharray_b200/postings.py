@@ -214,7 +214,7 @@ class SearchArray(ExtensionArray):
     @classmethod
     def index(cls, array, tokenizer=ws_tokenizer, truncate=False, batch_size=100000, avoid_copies=True,
               workers=4, cache_gt_than=25, data_dir: Optional[str] = None, autowarm=True,
-              device=0) -> "SearchArray":
+              device=0, gpu_build=False) -> "SearchArray":
         """Index an array of strings (reference postings.py:249-300).  batch_size / workers /
         cache_gt_than / data_dir / autowarm are accepted for signature compatibility: the
         per-term df table the reference warms lazily is computed on the device at upload.  data_dir:
@@ -222,7 +222,7 @@ class SearchArray(ExtensionArray):
         upload then DMAs straight from the mapping (cudaHostRegister), and a pickle carries the file name only."""
         if not is_list_like(array):
             raise TypeError("Expected list-like object, got {}".format(type(array)))
-        host = build_index(list(array), tokenizer, truncate=truncate)
+        host = build_index(list(array), tokenizer, truncate=truncate, gpu_build=device if gpu_build else None)
         if data_dir is not None:            # reference indexing.py:228-230, 291-293: memmap the bit positions
             host.memmap(data_dir)
         return cls.from_host_index(host, tokenizer=tokenizer, avoid_copies=avoid_copies, device=device)
