@@ -277,8 +277,8 @@ term_tile_kernel(const TermBatchArgs a) {
     //    derives the same tile bound; scores >= bound are this tile's candidates.
     const u32 k = a.topk.k;
     const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
+    const u32 M = tile_bound_width(k, hi - lo);
     if (need_bound) {
-        const u32 M = (k <= 10) ? 4u : 8u;
         u32 v = my_max;
         for (u32 r = 0; r < M; r++) {
             u32 m = warp_pop_max(v);
@@ -290,7 +290,7 @@ term_tile_kernel(const TermBatchArgs a) {
     float thr_f = 0.0f;
     if (k) {
         u32 thr = 1u;                                   // >= 1: skip zeros (scores are >= +0.0)
-        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
+        if (need_bound) thr = max(cta_kth_bound(s_top, k, M == 8u), 1u);
         thr_f = __uint_as_float(thr);
     }
     u64 *__restrict__ my_cand = nullptr;
@@ -392,7 +392,7 @@ dense_topk_tiles_kernel(float *__restrict__ dense, u64 stride, u32 row0, const T
         for (int e = 0; e < 4; e++)
             if (vs[e] > 0.0f) my_max = max(my_max, __float_as_uint(vs[e]));
     }
-    const u32 M = (k <= 10) ? 4u : 8u;
+    const u32 M = 8u;
     u32 mv = my_max;
     for (u32 r = 0; r < M; r++) {
         u32 m = warp_pop_max(mv);
@@ -400,7 +400,7 @@ dense_topk_tiles_kernel(float *__restrict__ dense, u64 stride, u32 row0, const T
     }
     if (tid == 0) { s_ncand = 0; s_tile_max = 0; }
     __syncthreads();
-    const float thr_f = __uint_as_float(max(cta_kth_bound(s_top, k), 1u));
+    const float thr_f = __uint_as_float(max(cta_kth_bound(s_top, k, true), 1u));
     u64 *__restrict__ my_cand = t.tile_cand + ((u64)q * t.n_tiles + tile) * t.slots;
     u32 cand_max = 0;
 #pragma unroll

@@ -84,10 +84,10 @@ __device__ __forceinline__ u32 warp_pop_max(u32 &v) {
 // k-th largest (k <= 32) of the CTA's thread maxima, from the per-warp top-M lists in shared
 // memory (M = 4 for k <= 10 else 8; exact unless one warp holds more than M of the CTA's top k).
 // Every warp computes it redundantly (~4k instructions... 4 per round), no extra barrier.
-__device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k) {
+__device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k, bool wide = false) {
     const unsigned lane = threadIdx.x & 31;
     u32 v0, v1 = 0;
-    if (k <= 10) {
+    if (k <= 10 && !wide) {
         v0 = s_top[(lane >> 2) * 8 + (lane & 3)];
     } else {
         v0 = s_top[lane];
@@ -131,7 +131,7 @@ __device__ __forceinline__ void tile_collect_ties_retry(const float *s_out, bool
             if (v == thr_f) best = max(best, 0xFFFFFFFFu - (g * 4 + e));
         }
     }
-    const u32 M = (t.k <= 10) ? 4u : 8u;
+    const u32 M = 8u;
     __syncthreads();                                // s_top may still be read by a slow warp of the first pass
     {
         u32 v = best;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void tile_collect_ties_retry(const float *s_out, bool
     }
     if (tid == 0) { *s_ncand = 0; *s_tile_max = 0; }
     __syncthreads();
-    const u32 kth = cta_kth_bound(s_top, t.k);      // 0: fewer than k threads hold a tie -> keep every tie
+    const u32 kth = cta_kth_bound(s_top, t.k, true);   // 0: fewer than k threads hold a tie -> keep every tie
     const u32 doc_bound = kth ? 0xFFFFFFFFu - kth : 0xFFFFFFFFu;
     u32 cand_max = 0;
 #pragma unroll
@@ -165,6 +165,11 @@ __device__ __forceinline__ void tile_collect_ties_retry(const float *s_out, bool
     __syncthreads();
 }
 
+// How many of its largest thread maxima every warp publishes for the tile bound.  4 per warp are enough for k <= 10
+// when all eight warps hold scores; a tile whose scores sit in two or three warps (a few dozen docs) must publish 8 per
+// warp, or fewer than k values exist, the bound degenerates to "keep everything" and 65+ docs overflow the 64 slots.
+__device__ __forceinline__ u32 tile_bound_width(u32 k, u32 n_items) { return (k <= 10 && n_items >= SA_TERM_THREADS) ? 4u : 8u; }
+
 // Flush one shared-memory score tile to its dense row with 16-byte streaming stores and, on the way,
 // collect the tile's top-k candidates (private slots, count, maximum): the same step the term kernel
 // ends with, shared with the phrase kernel.  `my_max` = largest score bits this thread put into the
@@ -176,8 +181,8 @@ __device__ __forceinline__ void flush_tile_collect(const float *s_out, float *__
     const u32 k = t.k;
     const u32 tile_doc0 = tile * SA_TILE_DOCS;
     const bool need_bound = k && n_items > k;                        // CTA-uniform
+    const u32 M = tile_bound_width(k, n_items);
     if (need_bound) {
-        const u32 M = (k <= 10) ? 4u : 8u;
         u32 v = my_max;
         for (u32 r = 0; r < M; r++) {
             u32 m = warp_pop_max(v);
@@ -189,7 +194,7 @@ __device__ __forceinline__ void flush_tile_collect(const float *s_out, float *__
     float thr_f = 0.0f;
     if (k) {
         u32 thr = 1u;
-        if (need_bound) thr = max(cta_kth_bound(s_top, k), 1u);
+        if (need_bound) thr = max(cta_kth_bound(s_top, k, M == 8u), 1u);
         thr_f = __uint_as_float(thr);
     }
     u64 *__restrict__ my_cand = k ? t.tile_cand + ((u64)row * t.n_tiles + tile) * t.slots : nullptr;

@@ -37,7 +37,7 @@ def test_large_memmap_upload_is_page_locked_in_place(tmp_path):
     """a > 32 MB words file goes to HBM by DMA from the (read-only) file mapping, or through pinned bounce buffers"""
     from oracle import search as osearch
     from searcharray_b200 import SearchArray, _lib, synth
-    spec = synth.SynthSpec(1_500_000, terms_per_bucket=3, n_phrases=8, n_bigrams=2)
+    spec = synth.SynthSpec(3_000_000, terms_per_bucket=3, n_phrases=8, n_bigrams=2)
     host, _, _ = synth.generate_shard(spec)
     host.avg_doc_length = synth.global_avg_doc_length(spec)
     assert host.words.nbytes > (32 << 20)
