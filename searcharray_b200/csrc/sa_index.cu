@@ -155,11 +155,11 @@ __global__ void tile_dir_kernel(const u64 *__restrict__ words, u64 n_words,
 // longest per-tile slice of every list that has a directory (sizes the merge regime's per-CTA scratch)
 __global__ void dir_max_kernel(const u32 *__restrict__ dir, const u64 *__restrict__ slot_dir_off, u32 n_slots, u32 n_tiles,
                                u32 *__restrict__ slot_max) {
-    const u32 slot = blockIdx.y;
+    const u32 slot = blockIdx.x;                 // (terms can outnumber the 65,535 limit of grid.y)
     if (slot >= n_slots || slot_dir_off[slot] == SA_NO_DIR) return;
     const u32 *d = dir + slot_dir_off[slot];
     u32 m = 0;
-    for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) m = max(m, d[t + 1] - d[t]);
+    for (u32 t = blockIdx.y * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.y * blockDim.x) m = max(m, d[t + 1] - d[t]);
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&slot_max[slot], m);
 }
@@ -418,7 +418,7 @@ extern "C" int sa_index_create(const uint64_t *words, uint64_t n_words,
         if (dir_words) {
             CREATE_CUDA(cudaMalloc(&d_slot_max, n_slots * sizeof(u32)));
             CREATE_CUDA(cudaMemsetAsync(d_slot_max, 0, n_slots * sizeof(u32), ix->stream));
-            dir_max_kernel<<<dim3(std::min<u32>(32, (n_tiles + 255) / 256), n_slots), 256, 0, ix->stream>>>(
+            dir_max_kernel<<<dim3(n_slots, std::min<u32>(32, (n_tiles + 255) / 256)), 256, 0, ix->stream>>>(
                 ix->d_tile_dir, d_slot_dir, n_slots, n_tiles, d_slot_max);
             CREATE_CUDA(cudaGetLastError());
             ix->stats.total_launches++;

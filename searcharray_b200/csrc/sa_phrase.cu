@@ -172,6 +172,8 @@ __device__ __forceinline__ Elem compute_elem(const u64 *__restrict__ D, u64 nD, 
     return e;
 }
 
+#include "sa_phrase_warp.cuh"
+
 struct StepShared {
     u32 warp_sums[PT / 32];
     u32 edoc[PT];
@@ -323,6 +325,12 @@ struct PhraseShared {
     u32 top[(PT / 32) * 8];
     u32 ncand, tile_max;
     __align__(8) u64 bar;
+    // merge regime: every warp's sub-slices of the staged segment and its result list
+    const u64 *wptr[PT / 32][SA_MAX_PHRASE_TERMS];
+    u32 wn[PT / 32][SA_MAX_PHRASE_TERMS];
+    u64 *wfin_docs[PT / 32];
+    u32 wfin_n[PT / 32];
+    u32 wcount[PT / 32];
 };
 
 // One (query, doc-range chunk) work item.
@@ -396,7 +404,7 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
     }
     __syncthreads();
     if (!P.ok) run = false;
-    u64 *contA = (STAGED ? cta_slab : a.arena + P.slab), *contB = contA + cap;
+    u64 *contA = (STAGED ? cta_slab : a.arena + P.slab), *contB = contA + cap;      // (STAGED: every warp has its own six buffers)
     u64 *docsA = contB + cap, *docsB = docsA + cap, *docsL = docsB + cap, *docsR = docsL + cap;
 
     // Runs one chain over terms [ta, tb).  lr: left-to-right (cont = RHS) else right-to-left.
@@ -548,86 +556,170 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
             __syncthreads();
         }
 
-        ChainResult fin;
-        fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
-        if (run && P.ok) {
-            if (pq.mode == SA_PHRASE_MODE_LR) {
-                fin = run_chain(0, n_terms, true, docsL);
-            } else if (pq.mode == SA_PHRASE_MODE_RL) {
-                fin = run_chain(0, n_terms, false, docsL);
-            } else {
-                // both chains always run (their pair statistics feed the speculation check)
-                ChainResult left = run_chain(0, pq.split, true, docsL);
-                fin = run_chain(pq.split, n_terms, false, docsR);
-                if (left.n_docs == 0) fin.n_docs = 0;
-                and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
-            }
-        }
-        // optional dump for the per-op parity export (single chunk, search regime)
-        if (!STAGED && a.dump.cont) {
-            for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
-            for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
-            if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
-        }
-
-        // 3. materialise the dense vector of the segment tile by tile (phrase_freqs[ids] = counts,
-        //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
-        //    streaming stores; the same pass collects the tile's top-k candidates.
-        // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
-        // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
-        // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
-        u64 cur = 0;
-        u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
-        for (u32 tile = ts; tile < te; tile++) {
-            const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
-            if (next_doc >= t_abs1) {
-                float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
-                if (a.topk.k && tid == 0) {
-                    const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
-                    a.topk.tile_cnt[t_idx] = 0;
-                    a.topk.tile_max[t_idx] = 0;
+        if (STAGED) {
+            // ---- merge regime: eight warps, eight doc sub-ranges of the segment, no block barrier inside the chain
+            if (run && P.ok) {
+                const u64 seg_docs = seg_d1 - seg_d0;
+                const u64 w_d0 = seg_d0 + seg_docs * warp / (PT / 32), w_d1 = seg_d0 + seg_docs * (warp + 1) / (PT / 32);
+                for (u32 t = 0; t < n_terms; t++) {
+                    const u64 *base = P.ptr[t];
+                    const u32 n = (u32)P.seg_n[t];
+                    const u32 lo = w_lower_bound_doc(base, n, w_d0);
+                    const u32 hi = lo + w_lower_bound_doc(base + lo, n - lo, w_d1);
+                    if (lane == 0) { P.wptr[warp][t] = base + lo; P.wn[warp][t] = hi - lo; }
                 }
-                continue;
+                __syncwarp();
+                const WarpFin wf = warp_phrase_chain(pq, P.wptr[warp], P.wn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
+                if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
+            } else if (lane == 0) {
+                P.wfin_docs[warp] = nullptr;
+                P.wfin_n[warp] = 0;
             }
-            // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
-            const u64 m0 = cur;
-            u64 lo = cur + 1, hi = fin.n_docs, st = 1;
-            while (lo < hi) {
-                const u64 probe = min(lo + st - 1, hi - 1);
-                if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
-                else { hi = probe; break; }
-            }
-            while (lo < hi) {
-                const u64 mid = (lo + hi) >> 1;
-                if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
-            }
-            const u64 m1 = lo;
-            cur = m1;
-            next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
+            __syncthreads();
+            // ---- materialise the segment's tiles: every warp scatters its own (sorted) result list
+            const u64 *wl = P.wfin_docs[warp];
+            const u32 wln = P.wfin_n[warp];
+            u32 wcur = 0;
+            for (u32 tile = ts; tile < te; tile++) {
+                const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
+                const u32 m0 = wcur;
+                u32 m1 = m0;
+                if (m0 < wln && (wl[m0] >> 32) < t_abs1) {
+                    u32 lo = m0 + 1, hi = wln, st = 1;
+                    while (lo < hi) {                       // gallop from the cursor, then bisect (warp-uniform)
+                        const u32 probe = min(lo + st - 1, hi - 1);
+                        if ((wl[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
+                        else { hi = probe; break; }
+                    }
+                    while (lo < hi) {
+                        const u32 mid = (lo + hi) >> 1;
+                        if ((wl[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+                    }
+                    m1 = lo;
+                }
+                wcur = m1;
+                if (lane == 0) P.wcount[warp] = m1 - m0;
+                __syncthreads();
+                u32 total = 0;
 #pragma unroll
-            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
-                reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
-            u32 my_max = 0, my_match = 0;
-            for (u64 i = m0 + tid; i < m1; i += PT) {
-                const u64 e = fin.docs[i];
-                const u32 c = (u32)(e & 0xFFFFFFFFull);
-                if (c == 0) continue;
-                const u64 d = (e >> 32) - a.doc_base;
-                if (d >= a.n_docs) continue;
-                my_match++;
-                const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
-                P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
-                if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+                for (int w = 0; w < PT / 32; w++) total += P.wcount[w];
+                if (total == 0) {
+                    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+                    if (a.topk.k && tid == 0) {
+                        const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                        a.topk.tile_cnt[t_idx] = 0;
+                        a.topk.tile_max[t_idx] = 0;
+                    }
+                    __syncthreads();                        // wcount is rewritten for the next tile
+                    continue;
+                }
+#pragma unroll
+                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+                    reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+                u32 my_max = 0, my_match = 0;
+                for (u32 i = m0 + lane; i < m1; i += 32) {
+                    const u64 e = wl[i];
+                    const u32 c = (u32)(e & 0xFFFFFFFFull);
+                    if (c == 0) continue;
+                    const u64 d = (e >> 32) - a.doc_base;
+                    if (d >= a.n_docs) continue;
+                    my_match++;
+                    const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+                    P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
+                    if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+                }
+                my_match = __reduce_add_sync(0xffffffffu, my_match);
+                if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+                __syncthreads();
+                flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, total,
+                                   P.top, &P.ncand, &P.tile_max);
             }
-            my_match = __reduce_add_sync(0xffffffffu, my_match);
-            if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
-            __syncthreads();
-            flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
-                               P.top, &P.ncand, &P.tile_max);
+        } else {
+        ChainResult fin;
+            fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
+            if (run && P.ok) {
+                if (pq.mode == SA_PHRASE_MODE_LR) {
+                    fin = run_chain(0, n_terms, true, docsL);
+                } else if (pq.mode == SA_PHRASE_MODE_RL) {
+                    fin = run_chain(0, n_terms, false, docsL);
+                } else {
+                    // both chains always run (their pair statistics feed the speculation check)
+                    ChainResult left = run_chain(0, pq.split, true, docsL);
+                    fin = run_chain(pq.split, n_terms, false, docsR);
+                    if (left.n_docs == 0) fin.n_docs = 0;
+                    and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
+                }
+            }
+            // optional dump for the per-op parity export (single chunk, search regime)
+            if (!STAGED && a.dump.cont) {
+                for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
+                for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
+                if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
+            }
+    
+            // 3. materialise the dense vector of the segment tile by tile (phrase_freqs[ids] = counts,
+            //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
+            //    streaming stores; the same pass collects the tile's top-k candidates.
+            // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
+            // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
+            // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
+            u64 cur = 0;
+            u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
+            for (u32 tile = ts; tile < te; tile++) {
+                const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
+                if (next_doc >= t_abs1) {
+                    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+                    for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+                    if (a.topk.k && tid == 0) {
+                        const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                        a.topk.tile_cnt[t_idx] = 0;
+                        a.topk.tile_max[t_idx] = 0;
+                    }
+                    continue;
+                }
+                // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
+                const u64 m0 = cur;
+                u64 lo = cur + 1, hi = fin.n_docs, st = 1;
+                while (lo < hi) {
+                    const u64 probe = min(lo + st - 1, hi - 1);
+                    if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
+                    else { hi = probe; break; }
+                }
+                while (lo < hi) {
+                    const u64 mid = (lo + hi) >> 1;
+                    if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+                }
+                const u64 m1 = lo;
+                cur = m1;
+                next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
+    #pragma unroll
+                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+                    reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+                u32 my_max = 0, my_match = 0;
+                for (u64 i = m0 + tid; i < m1; i += PT) {
+                    const u64 e = fin.docs[i];
+                    const u32 c = (u32)(e & 0xFFFFFFFFull);
+                    if (c == 0) continue;
+                    const u64 d = (e >> 32) - a.doc_base;
+                    if (d >= a.n_docs) continue;
+                    my_match++;
+                    const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+                    P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
+                    if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+                }
+                my_match = __reduce_add_sync(0xffffffffu, my_match);
+                if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+                __syncthreads();
+                flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
+                                   P.top, &P.ncand, &P.tile_max);
+            }
         }
         __syncthreads();                    // every read of the staged slices / the slab is done before the next segment
         ts = te;
@@ -655,7 +747,7 @@ phrase_staged_kernel(const PhraseArgs a) {
     }
     __syncthreads();
     u32 phase = 0;
-    u64 *slab = a.slabs + (u64)blockIdx.x * 6ull * a.slab_cap;
+    u64 *slab = a.slabs + (u64)blockIdx.x * (PT / 32) * 6ull * a.slab_cap;      // six buffers for each of the CTA's warps
     const u32 n_work = a.n_sel * a.n_chunks;
     for (;;) {
         __syncthreads();
@@ -934,7 +1026,7 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
     const u32 stage_words = sa_phrase_stage_words();
     u32 ctas = 0;
     if ((rc = staged_grid(ix, stage_words, &ctas))) return rc;
-    if ((rc = ix->phrase_slabs.reserve((size_t)ctas * 6 * split->slab_cap * sizeof(u64)))) return rc;
+    if ((rc = ix->phrase_slabs.reserve((size_t)ctas * (PT / 32) * 6 * split->slab_cap * sizeof(u64)))) return rc;
     a.qsel = split->d_staged;
     a.n_sel = split->n_staged;
     a.n_chunks = split->staged_chunks;

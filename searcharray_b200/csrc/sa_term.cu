@@ -198,7 +198,7 @@ term_tile_kernel(const TermBatchArgs a) {
         //     lane takes FOUR records with one 16-byte load (record runs start 16-byte aligned; the slice is
         //     widened to whole quads and the strangers masked); no run detection, no shuffles, no popcount.
         const u32 *__restrict__ recs = a.recs + tq.rec_off;
-        if (hi - lo >= SA_TERM_THREADS * 4) {
+        if (hi - lo >= 128u) {             // >= 32 quads; with a tile bound over thread maxima at most 4 * k docs reach it
             for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
                 const u32 i = base + tid * 4;
                 uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
