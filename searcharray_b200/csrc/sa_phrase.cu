@@ -35,6 +35,7 @@ int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bo
 int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
 
 #define PT SA_PHRASE_THREADS
+#define PW_FB 240        // filtered words kept per term and tile by the merge regime's candidate compaction
 
 static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks);
 
@@ -326,11 +327,12 @@ struct PhraseShared {
     u32 ncand, tile_max;
     __align__(8) u64 bar;
     // merge regime: every warp's sub-slices of the staged segment and its result list
-    const u64 *wptr[PT / 32][SA_MAX_PHRASE_TERMS];
-    u32 wn[PT / 32][SA_MAX_PHRASE_TERMS];
+    const u64 *wptr[2][SA_MAX_PHRASE_TERMS];                    // [0] every term's slice of the current tile, [1] the filtered copies
+    u32 wn[2][SA_MAX_PHRASE_TERMS];
+    const u64 *sptr[PT / 32][SA_MAX_PHRASE_TERMS];              // every warp's sub-slices (dense conjunctions)
+    u32 sn[PT / 32][SA_MAX_PHRASE_TERMS];
     u64 *wfin_docs[PT / 32];
     u32 wfin_n[PT / 32];
-    u32 wcount[PT / 32];
 };
 
 // One (query, doc-range chunk) work item.
@@ -557,52 +559,124 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
         }
 
         if (STAGED) {
-            // ---- merge regime: eight warps, eight doc sub-ranges of the segment, no block barrier inside the chain
-            if (run && P.ok) {
-                const u64 seg_docs = seg_d1 - seg_d0;
-                const u64 w_d0 = seg_d0 + seg_docs * warp / (PT / 32), w_d1 = seg_d0 + seg_docs * (warp + 1) / (PT / 32);
-                for (u32 t = 0; t < n_terms; t++) {
-                    const u64 *base = P.ptr[t];
-                    const u32 n = (u32)P.seg_n[t];
-                    const u32 lo = w_lower_bound_doc(base, n, w_d0);
-                    const u32 hi = lo + w_lower_bound_doc(base + lo, n - lo, w_d1);
-                    if (lane == 0) { P.wptr[warp][t] = base + lo; P.wn[warp][t] = hi - lo; }
-                }
-                __syncwarp();
-                const WarpFin wf = warp_phrase_chain(pq, P.wptr[warp], P.wn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
-                if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
-            } else if (lane == 0) {
-                P.wfin_docs[warp] = nullptr;
-                P.wfin_n[warp] = 0;
-            }
-            __syncthreads();
-            // ---- materialise the segment's tiles: every warp scatters its own (sorted) result list
-            const u64 *wl = P.wfin_docs[warp];
-            const u32 wln = P.wfin_n[warp];
-            u32 wcur = 0;
+            // ---- merge regime, tile by tile.  A doc can only match if it holds EVERY term of the phrase, so each tile
+            //      first builds one doc-presence bitmap per term from the staged slices (shared-memory atomicOr), ANDs them,
+            //      and only the candidate docs' words (compacted in order, by ballots) enter the bigram chain -- which one
+            //      warp then runs on a few dozen words.  Conjunctions of common terms are rare (df/N of .3, .1, .03, .01:
+            //      9e-6 of the docs), so almost every tile ends at the AND: the lists are streamed once and that is all.
+            //      The pair statistics (same-term speculation) then cover the candidate docs only; sa_phrase.cu's host side
+            //      treats any disagreement with the guess as "re-run exactly" (see sa_phrase_run_sync), which keeps this sound.
+            u32 *cand_bm = reinterpret_cast<u32 *>(P.tile);                      // [256] candidate docs of the tile
+            u32 *term_bm = cand_bm + SA_TILE_DOCS / 32;                           // [n_terms][256], dead once cand_bm exists
+            u64 *fb = reinterpret_cast<u64 *>(cand_bm + SA_TILE_DOCS / 32);       // [n_terms][PW_FB] filtered words (overlays term_bm)
             for (u32 tile = ts; tile < te; tile++) {
-                const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
-                const u32 m0 = wcur;
-                u32 m1 = m0;
-                if (m0 < wln && (wl[m0] >> 32) < t_abs1) {
-                    u32 lo = m0 + 1, hi = wln, st = 1;
-                    while (lo < hi) {                       // gallop from the cursor, then bisect (warp-uniform)
-                        const u32 probe = min(lo + st - 1, hi - 1);
-                        if ((wl[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
-                        else { hi = probe; break; }
+                const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
+                const u64 td1 = min(td0 + SA_TILE_DOCS, dend);
+                bool have_all = run && P.ok;
+                if (have_all) {
+                    for (u32 t = warp; t < n_terms; t += PT / 32) {
+                        const u64 *base = P.ptr[t];
+                        const u32 n = (u32)P.seg_n[t];
+                        u32 lo = 0, hi = n;
+                        if (te - ts > 1) {
+                            lo = w_lower_bound_doc(base, n, td0);
+                            hi = lo + w_lower_bound_doc(base + lo, n - lo, td1);
+                        }
+                        if (lane == 0) { P.wptr[0][t] = base + lo; P.wn[0][t] = hi - lo; }
                     }
-                    while (lo < hi) {
-                        const u32 mid = (lo + hi) >> 1;
-                        if ((wl[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
-                    }
-                    m1 = lo;
+                    __syncthreads();
+                    for (u32 t = 0; t < n_terms; t++) have_all = have_all && P.wn[0][t] > 0;
                 }
-                wcur = m1;
-                if (lane == 0) P.wcount[warp] = m1 - m0;
+                u32 n_cand = 0;
+                bool filtered = false;
+                if (have_all) {                                                  // CTA-uniform
+                    for (u32 i = tid; i < n_terms * (SA_TILE_DOCS / 32); i += PT) term_bm[i] = 0u;
+                    if (tid == 0) P.ncand = 0;
+                    __syncthreads();
+                    for (u32 t = 0; t < n_terms; t++) {
+                        const u64 *lst = P.wptr[0][t];
+                        const u32 n = P.wn[0][t];
+                        u32 *bm = term_bm + t * (SA_TILE_DOCS / 32);
+                        for (u32 i = tid; i < n; i += PT) {
+                            const u32 rel = (u32)((lst[i] >> SA_KEY_SHIFT) - td0);
+                            atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
+                        }
+                    }
+                    __syncthreads();
+                    {
+                        u32 c = term_bm[tid];
+                        for (u32 t = 1; t < n_terms; t++) c &= term_bm[t * (SA_TILE_DOCS / 32) + tid];
+                        const u32 cnt = __reduce_add_sync(0xffffffffu, (u32)__popc(c));
+                        if (lane == 0 && cnt) atomicAdd(&P.ncand, cnt);
+                        __syncthreads();                                         // every term_bm word is read before cand_bm / fb overwrite the region
+                        cand_bm[tid] = c;
+                    }
+                    __syncthreads();
+                    n_cand = P.ncand;
+                    if (n_cand) {
+                        // ordered compaction of the candidate docs' words, one warp per term
+                        for (u32 t = warp; t < n_terms; t += PT / 32) {
+                            const u64 *lst = P.wptr[0][t];
+                            const u32 n = P.wn[0][t];
+                            u64 *dst = fb + (u64)t * PW_FB;
+                            u32 cnt = 0;
+                            for (u32 i0 = 0; i0 < n; i0 += 32) {
+                                const u32 i = i0 + lane;
+                                u64 w = 0;
+                                bool keep = false;
+                                if (i < n) {
+                                    w = lst[i];
+                                    const u32 rel = (u32)((w >> SA_KEY_SHIFT) - td0);
+                                    keep = (cand_bm[rel >> 5] >> (rel & 31u)) & 1u;
+                                }
+                                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                                const u32 at = cnt + __popc(m & ((1u << lane) - 1u));
+                                if (keep && at < PW_FB) dst[at] = w;
+                                cnt += __popc(m);
+                            }
+                            if (lane == 0) P.wn[1][t] = cnt;
+                        }
+                        __syncthreads();
+                        filtered = true;
+                        for (u32 t = 0; t < n_terms; t++) filtered = filtered && P.wn[1][t] <= PW_FB;
+                    }
+                }
+                // ---- the chain
+                if (n_cand && filtered) {
+                    if (warp == 0) {                                             // a few dozen words: one warp
+                        if (lane < n_terms) { P.wptr[1][lane] = fb + (u64)lane * PW_FB; }
+                        __syncwarp();
+                        const WarpFin wf = warp_phrase_chain(pq, P.wptr[1], P.wn[1], cta_slab, cap, &a.stats[q]);
+                        if (lane == 0) { P.wfin_docs[0] = wf.docs; P.wfin_n[0] = wf.n_docs; }
+                    } else if (lane == 0) {
+                        P.wfin_docs[warp] = nullptr;
+                        P.wfin_n[warp] = 0;
+                    }
+                } else if (n_cand) {
+                    // too many candidates to compact (dense conjunctions): eight warps, eight doc sub-ranges of the tile
+                    const u64 t_docs = td1 - td0;
+                    const u64 w_d0 = td0 + t_docs * warp / (PT / 32), w_d1 = td0 + t_docs * (warp + 1) / (PT / 32);
+                    for (u32 t = 0; t < n_terms; t++) {
+                        const u64 *base = P.wptr[0][t];
+                        const u32 n = P.wn[0][t];
+                        const u32 lo = w_lower_bound_doc(base, n, w_d0);
+                        const u32 hi = lo + w_lower_bound_doc(base + lo, n - lo, w_d1);
+                        if (lane == 0) { P.sptr[warp][t] = base + lo; P.sn[warp][t] = hi - lo; }
+                    }
+                    __syncwarp();
+                    const WarpFin wf = warp_phrase_chain(pq, P.sptr[warp], P.sn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
+                    if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
+                } else if (lane == 0) {
+                    P.wfin_docs[warp] = nullptr;
+                    P.wfin_n[warp] = 0;
+                }
                 __syncthreads();
+                // ---- materialise the tile: every warp scatters its own (sorted) result list
+                const u64 *wl = P.wfin_docs[warp];
+                const u32 wln = P.wfin_n[warp];
                 u32 total = 0;
 #pragma unroll
-                for (int w = 0; w < PT / 32; w++) total += P.wcount[w];
+                for (int w = 0; w < PT / 32; w++) total += P.wfin_n[w];
                 if (total == 0) {
                     float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -613,7 +687,7 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
                         a.topk.tile_cnt[t_idx] = 0;
                         a.topk.tile_max[t_idx] = 0;
                     }
-                    __syncthreads();                        // wcount is rewritten for the next tile
+                    __syncthreads();                        // the per-warp result slots are rewritten for the next tile
                     continue;
                 }
 #pragma unroll
@@ -621,7 +695,7 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
                     reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncthreads();
                 u32 my_max = 0, my_match = 0;
-                for (u32 i = m0 + lane; i < m1; i += 32) {
+                for (u32 i = lane; i < wln; i += 32) {
                     const u64 e = wl[i];
                     const u32 c = (u32)(e & 0xFFFFFFFFull);
                     if (c == 0) continue;
@@ -882,7 +956,9 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         arena_words += 6 * (sum + 2ull * n_chunks);
     }
     // merge regime (single query on the index's own lists): persistent CTAs + TMA staging, no bump arena
-    const bool staged = staged_slab_cap && Q == 1 && d_words == ix->d_words && !dump.cont && sa_phrase_is_staged(pqs[0]);
+    bool staged = staged_slab_cap && Q == 1 && d_words == ix->d_words && !dump.cont && sa_phrase_is_staged(pqs[0]);
+    const u64 full_arena_words = arena_words;
+    const std::vector<PhraseQuery> pqs_in = pqs;
     if (staged) arena_words = 64;
     if ((rc = ix->phrase_scratch.reserve(arena_words * sizeof(u64) + 64))) return rc;
     unsigned long long *d_used = (unsigned long long *)ix->phrase_scratch.p;
@@ -947,6 +1023,17 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
             }
         }
         if (!again) return SA_OK;
+        if (staged) {
+            // The merge regime counts equal-header pairs in the candidate docs only (docs holding every term): enough to
+            // CONFIRM a guess, not to derive the reference's global same-term decision from.  On any disagreement the
+            // query starts over in the search regime, whose statistics cover every pair.
+            staged = false;
+            pqs = pqs_in;
+            arena_words = full_arena_words;
+            if ((rc = ix->phrase_scratch.reserve(arena_words * sizeof(u64) + 64))) return rc;
+            d_used = (unsigned long long *)ix->phrase_scratch.p;
+            d_arena = (u64 *)ix->phrase_scratch.p + 8;
+        }
     }
     sa_set_error("same-term speculation did not converge");
     return SA_ERR_ARG;

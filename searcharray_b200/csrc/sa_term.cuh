@@ -72,18 +72,21 @@ void sa_batch_dims(sa_index *ix, u32 *nq, u32 *k);
 void sa_unpack_keys(const u64 *keys, u64 n, uint32_t *out_docs, float *out_scores);
 
 #ifdef __CUDACC__
-// The j-th round of "take the warp maximum, then clear it" (REDUX.MAX: one instruction per
-// round on sm_80+).  Equal values collapse into one, which can only lower the resulting bound
-// -- it stays a valid lower bound of the k-th best score.
+// The j-th round of "take the warp maximum, then clear it" (REDUX.MAX: one instruction per round on sm_80+).
+// Exactly ONE lane gives up its value per round, so equal values are counted with their multiplicity: BM25
+// scores are a function of (tf, doc length) only and repeat a lot -- collapsing duplicates used to leave fewer
+// than k published values on tiles whose top scores tie, which degenerates the bound to "keep everything".
 __device__ __forceinline__ u32 warp_pop_max(u32 &v) {
-    u32 m = __reduce_max_sync(0xffffffffu, v);
-    if (v == m) v = 0;
+    const u32 m = __reduce_max_sync(0xffffffffu, v);
+    const unsigned holders = __ballot_sync(0xffffffffu, v == m);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(holders) - 1)) v = 0;
     return m;
 }
 
-// k-th largest (k <= 32) of the CTA's thread maxima, from the per-warp top-M lists in shared
-// memory (M = 4 for k <= 10 else 8; exact unless one warp holds more than M of the CTA's top k).
-// Every warp computes it redundantly (~4k instructions... 4 per round), no extra barrier.
+// k-th largest (k <= 32), with multiplicity, of the CTA's thread maxima, from the per-warp top-M lists in shared
+// memory (M = 4 or 8, tile_bound_width; exact unless one warp holds more than M of the CTA's top k, in which case
+// the result is smaller -- still a valid lower bound of the tile's k-th best score, because thread maxima belong to
+// distinct docs).  Every warp computes it redundantly, no extra barrier.
 __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k, bool wide = false) {
     const unsigned lane = threadIdx.x & 31;
     u32 v0, v1 = 0;
@@ -95,15 +98,16 @@ __device__ __forceinline__ u32 cta_kth_bound(const u32 *s_top /*[8][8]*/, u32 k,
     }
     u32 kth = 0;
     for (u32 r = 0; r < k; r++) {
-        u32 m0 = __reduce_max_sync(0xffffffffu, max(v0, v1));
-        if (v0 == m0) v0 = 0;
-        else if (v1 == m0) v1 = 0;
+        const u32 m0 = __reduce_max_sync(0xffffffffu, max(v0, v1));
         kth = m0;
         if (m0 == 0) break;
+        const unsigned holders = __ballot_sync(0xffffffffu, v0 == m0 || v1 == m0);
+        if (lane == (unsigned)(__ffs(holders) - 1)) {        // one holder gives up ONE copy
+            if (v0 == m0) v0 = 0; else v1 = 0;
+        }
     }
     return kth;
 }
-
 
 // Candidate-slot overflow caused by TIES at the tile bound (BM25 scores are a function of (tf, doc_len) only, so
 // exact ties among thousands of docs are normal): the tile is still in shared memory, so the CTA collects
