@@ -35,7 +35,7 @@ int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bo
 int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
 
 #define PT SA_PHRASE_THREADS
-#define PW_FB 240        // filtered words kept per term and tile by the merge regime's candidate compaction
+#define PW_WARP_WORDS 496 // words of compaction area per warp in the merge regime ((32 KB tile - 1 KB candidate bitmap) / 8 warps)
 
 static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks);
 
@@ -313,101 +313,77 @@ __device__ void and_min(u64 *__restrict__ cur, u64 n_cur, const u64 *__restrict_
 
 struct ChainResult { u64 *docs; u64 n_docs; u64 *cont; u64 n_cont; };
 
-// Shared state of one CTA of the phrase kernels.
-struct PhraseShared {
-    StepShared S;
-    u64 lo[SA_MAX_PHRASE_TERMS], n[SA_MAX_PHRASE_TERMS];        // this CTA's doc-range chunk: slice of every term's list
-    const u64 *ptr[SA_MAX_PHRASE_TERMS];                        // current segment: where each term's slice is read from
-    u64 seg_lo[SA_MAX_PHRASE_TERMS], seg_n[SA_MAX_PHRASE_TERMS];
-    u64 slab;
-    int ok;
-    u32 seg_te, any_staged, work;
-    __align__(16) float tile[SA_TILE_DOCS];
-    u32 top[(PT / 32) * 8];
-    u32 ncand, tile_max;
-    __align__(8) u64 bar;
-    // merge regime: every warp's sub-slices of the staged segment and its result list
-    const u64 *wptr[2][SA_MAX_PHRASE_TERMS];                    // [0] every term's slice of the current tile, [1] the filtered copies
-    u32 wn[2][SA_MAX_PHRASE_TERMS];
-    const u64 *sptr[PT / 32][SA_MAX_PHRASE_TERMS];              // every warp's sub-slices (dense conjunctions)
-    u32 sn[PT / 32][SA_MAX_PHRASE_TERMS];
-    u64 *wfin_docs[PT / 32];
-    u32 wfin_n[PT / 32];
-};
+// ---------------------------------------------------------------------------------------------------------------
+// The SEARCH regime (|shortest list| << |the others|): one CTA per (query, doc-range chunk) runs the whole chain once
+// over its chunk; a step's driver elements binary-search the other list in global memory, which skips most of it.
+__global__ void __launch_bounds__(PT, 4)
+phrase_kernel(const PhraseArgs a) {
+    __shared__ StepShared S;
+    __shared__ u64 s_lo[SA_MAX_PHRASE_TERMS], s_n[SA_MAX_PHRASE_TERMS];
+    __shared__ u64 s_slab;
+    __shared__ int s_ok;
+    __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
+    __shared__ u32 s_top[(PT / 32) * 8];
+    __shared__ u32 s_ncand, s_tile_max;
 
-// One (query, doc-range chunk) work item.
-//
-// STAGED == false -- the search regime (|shortest list| << |the others|): the chain runs once over the whole
-//   chunk; a step's driver elements binary-search the other list in global memory, which skips most of it.
-// STAGED == true -- the merge regime (balanced lists; chosen per query by the host, sa_phrase_is_staged): the
-//   chunk is cut into SEGMENTS of whole tiles whose posting slices fit in the CTA's staging buffer; one elected
-//   thread copies every term's slice of the segment into shared memory with TMA bulk copies
-//   (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes), the CTA waits on the mbarrier, and the
-//   same chain then runs with every search hitting shared memory: each list is read from HBM exactly once,
-//   sequentially (the 8 * sum(W) of B_phrase), and the continuation lists stay in a per-CTA slab that lives in
-//   L2.  A slice that does not fit (a tile of a very dense term) is simply read from global memory.
-template <bool STAGED>
-__device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, PhraseShared &P, u64 *stage,
-                            u32 &bar_phase, u64 *cta_slab, u64 cta_slab_cap) {
+    // grid = (queries, chunks): neighbouring CTAs belong to different queries (see term_tile_kernel)
+    const u32 q = a.qsel ? a.qsel[blockIdx.x] : blockIdx.x;
+    const u32 chunk = blockIdx.y;
     const PhraseQuery &pq = a.queries[q];
     const u32 n_terms = pq.n_terms;
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u64 d0 = a.doc_base + (u64)chunk * a.docs_per_chunk;
     const u64 dend = a.doc_base + a.n_docs;
-    if (d0 >= dend) return;                    // (grids are sized so this does not happen)
+    if (d0 >= dend) return;                    // (grid is sized so this does not happen)
     const u64 d1 = min(d0 + a.docs_per_chunk, dend);
-    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
-    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
-    StepShared &S = P.S;
+    ChainResult fin;
+    fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
+    bool run = true;
 
-    // 1. every term's slice for this CTA's doc range (tile directory when the list has one)
-    __syncthreads();                            // (persistent CTAs: the previous work item is done with P)
+    // 1. every term's slice for this doc range
     for (u32 t = warp; t < n_terms; t += PT / 32) {
         const u64 *lst = a.words + pq.off[t];
         u64 lo, hi;
-        if (pq.dir_plus1[t] && a.tile_dir) {
+        if (pq.dir_plus1[t] && a.tile_dir) {               // chunks are whole tiles: the list's tile directory has the slice
             const u32 *dir = a.tile_dir + (pq.dir_plus1[t] - 1);
-            lo = __ldg(dir + tile0);
-            hi = __ldg(dir + tile1);
+            lo = __ldg(dir + (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS));
+            hi = __ldg(dir + (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS));
         } else {
             lo = warp_lower_bound_shifted(lst, 0, pq.len[t], d0, SA_KEY_SHIFT);
             hi = warp_lower_bound_shifted(lst, lo, pq.len[t], d1, SA_KEY_SHIFT);
         }
-        if (lane == 0) { P.lo[t] = lo; P.n[t] = hi - lo; }
+        if (lane == 0) { s_lo[t] = lo; s_n[t] = hi - lo; }
     }
     __syncthreads();
     u64 cap = 0, widest = 0;
     for (u32 t = 0; t < n_terms; t++) {
-        cap = max(cap, P.n[t]);
-        if (P.n[t]) widest++;
+        cap = max(cap, s_n[t]);
+        if (s_n[t]) widest++;
     }
     // A chunk where fewer than two terms occur has no pairs at any step.  (A chunk that merely
     // misses ONE term must still run its earlier steps: their pairs count towards the global
     // same-term decision of the reference.)
-    bool run = widest >= 2;
+    if (widest < 2) run = false;
     cap += 2;
 
-    // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers.  Bound: a step's continuation words carry
-    //    distinct headers of the NEW term's slice and its (doc, count) entries come from distinct driver elements,
-    //    so `longest slice + 2` entries per buffer always suffice.
-    if (STAGED) {
-        cap = cta_slab_cap;                    // per-CTA slab, sized by the host from the per-tile maxima
-        if (tid == 0) { P.ok = 1; P.slab = 0; }
-    } else if (tid == 0) {
-        P.ok = 1;
-        P.slab = 0;
+    // 2. scratch slab: 2 continuation buffers + 4 (doc,count) buffers
+    if (tid == 0) {
+        s_ok = 1;
+        s_slab = 0;
         if (run) {
             unsigned long long need = 6ull * cap;
             unsigned long long at = atomicAdd(a.arena_used, need);
-            P.ok = (at + need <= a.arena_cap);
-            P.slab = at;
-            if (!P.ok) atomicExch(&a.stats[q].overflow, 1u);
+            s_ok = (at + need <= a.arena_cap);
+            s_slab = at;
+            if (!s_ok) atomicExch(&a.stats[q].overflow, 1u);
         }
     }
     __syncthreads();
-    if (!P.ok) run = false;
-    u64 *contA = (STAGED ? cta_slab : a.arena + P.slab), *contB = contA + cap;      // (STAGED: every warp has its own six buffers)
+    if (!s_ok) run = false;
+    u64 *contA = a.arena + s_slab, *contB = contA + cap;
     u64 *docsA = contB + cap, *docsB = docsA + cap, *docsL = docsB + cap, *docsR = docsL + cap;
+
+    auto slice = [&](u32 t) { return a.words + pq.off[t] + s_lo[t]; };
 
     // Runs one chain over terms [ta, tb).  lr: left-to-right (cont = RHS) else right-to-left.
     auto run_chain = [&](u32 ta, u32 tb, bool lr, u64 *final_docs) -> ChainResult {
@@ -416,8 +392,8 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
         res.n_docs = 0;
         res.cont = contA;
         res.n_cont = 0;
-        const u64 *carry = lr ? P.ptr[ta] : P.ptr[tb - 1];
-        u64 n_carry = lr ? P.seg_n[ta] : P.seg_n[tb - 1];
+        const u64 *carry = lr ? slice(ta) : slice(tb - 1);
+        u64 n_carry = lr ? s_n[ta] : s_n[tb - 1];
         u64 *cont_bufs[2] = {contA, contB};
         u64 *doc_bufs[2] = {docsA, docsB};
         int flip = 0;
@@ -427,8 +403,8 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
         for (u32 s = 0; s < n_steps; s++) {
             const u32 tnew = lr ? (ta + 1 + s) : (tb - 2 - s);     // also the step id
             const bool same = (pq.same_guess >> tnew) & 1u;
-            const u64 *other = P.ptr[tnew];
-            const u64 n_other = P.seg_n[tnew];
+            const u64 *other = slice(tnew);
+            const u64 n_other = s_n[tnew];
             if (n_carry == 0 || n_other == 0) {   // no pairs from here on in this doc range
                 res.n_docs = 0;
                 res.n_cont = 0;
@@ -470,357 +446,414 @@ __device__ void phrase_work(const PhraseArgs &a, const u32 q, const u32 chunk, P
         return res;
     };
 
+    if (run) {
+    if (pq.mode == SA_PHRASE_MODE_LR) {
+        fin = run_chain(0, n_terms, true, docsL);
+    } else if (pq.mode == SA_PHRASE_MODE_RL) {
+        fin = run_chain(0, n_terms, false, docsL);
+    } else {
+        // both chains always run (their pair statistics feed the speculation check)
+        ChainResult left = run_chain(0, pq.split, true, docsL);
+        fin = run_chain(pq.split, n_terms, false, docsR);
+        if (left.n_docs == 0) fin.n_docs = 0;
+        and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
+    }
+
+    }
+    // optional dump for the per-op parity export (single chunk)
+    if (a.dump.cont) {
+        for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
+        for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
+        if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
+    }
+
+    // 3. materialise the dense vector of this doc range tile by tile (phrase_freqs[ids] = counts,
+    //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
+    //    streaming stores; the same pass collects the tile's top-k candidates.
+    float *out = a.out + (u64)q * a.out_stride;
+    Bm25Params p = a.bm25;
+    p.idf = pq.idf;
+    const u32 row = a.topk_row0 + q;
+    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
+    // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
+    // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
+    u64 cur = 0;
+    u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
+    for (u32 tile = tile0; tile < tile1; tile++) {
+        const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
+        if (next_doc >= t_abs1) {
+            float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+            if (a.topk.k && tid == 0) {
+                const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                a.topk.tile_cnt[t_idx] = 0;
+                a.topk.tile_max[t_idx] = 0;
+            }
+            continue;
+        }
+        // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
+        const u64 m0 = cur;
+        u64 lo = cur + 1, hi = fin.n_docs, st = 1;
+        while (lo < hi) {
+            const u64 probe = min(lo + st - 1, hi - 1);
+            if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
+            else { hi = probe; break; }
+        }
+        while (lo < hi) {
+            const u64 mid = (lo + hi) >> 1;
+            if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
+        }
+        const u64 m1 = lo;
+        cur = m1;
+        next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+            reinterpret_cast<float4 *>(s_tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        u32 my_max = 0, my_match = 0;
+        for (u64 i = m0 + tid; i < m1; i += PT) {
+            const u64 e = fin.docs[i];
+            const u32 c = (u32)(e & 0xFFFFFFFFull);
+            if (c == 0) continue;
+            const u64 d = (e >> 32) - a.doc_base;
+            if (d >= a.n_docs) continue;
+            my_match++;
+            const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+            s_tile[d - (u64)tile * SA_TILE_DOCS] = v;
+            if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+        }
+        my_match = __reduce_add_sync(0xffffffffu, my_match);
+        if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+        __syncthreads();
+        flush_tile_collect(s_tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
+                           (u32)min(m1 - m0, (u64)PT), s_top, &s_ncand, &s_tile_max);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// The MERGE regime (balanced lists; chosen per query by the host, sa_phrase_is_staged): persistent CTAs, each claiming
+// (query, 16-tile chunk) work items.  A work item is cut into SEGMENTS of whole tiles whose posting slices fit in one
+// half of the CTA's staging buffer.  Warp 0 plans a segment from the chunk's tile-directory entries (preloaded into
+// shared memory) and its lane 0 arms an mbarrier and issues one TMA bulk copy per term
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes); the NEXT segment is planned and issued into
+// the other half before the current one is consumed, so the copy engine streams every list from HBM exactly once,
+// sequentially, while the SM works (double buffering).  Per tile:
+//   1. a doc can only match if it holds EVERY term, so each term's slice sets bits in a doc-presence bitmap
+//      (shared-memory atomicOr) and the bitmaps are ANDed.  Conjunctions of common terms are rare (df/N of .3, .1,
+//      .03, .01: 9e-6 of the docs), so almost every tile ends here and is written as zeros;
+//   2. otherwise each of the eight warps takes 1,024 docs of the tile: it compacts the candidate docs' words of
+//      every term in order (ballots) and runs the whole bigram chain on them at warp scope (sa_phrase_warp.cuh);
+//   3. the tile is materialised (zeros + BM25-scored matches) and its top-k candidates collected.
+// The pair statistics of the same-term speculation cover the candidate docs only -- enough to CONFIRM a guess, not
+// to derive the reference's global decision from; any disagreement re-runs the query in the search regime
+// (sa_phrase_run_sync / redo_query), which keeps the result exact.
+#define PS_MAX_CHUNK_TILES 32
+
+struct SegPlan {                                   // one per staging-buffer half
+    u32 te, any;
+    u32 n[SA_MAX_PHRASE_TERMS];                    // words of each term in the segment
+    u32 dir0[SA_MAX_PHRASE_TERMS];                 // directory entry of the segment's first tile (tile slices by subtraction)
+    const u64 *ptr[SA_MAX_PHRASE_TERMS];           // where the segment's slice is read from (staged copy, or global)
+};
+
+struct StagedShared {
+    u32 dirs[SA_MAX_PHRASE_TERMS][PS_MAX_CHUNK_TILES + 1];   // tile-directory entries of the chunk's tile boundaries
+    u32 has_dir[SA_MAX_PHRASE_TERMS];
+    u64 c_lo[SA_MAX_PHRASE_TERMS], c_n[SA_MAX_PHRASE_TERMS];  // chunk slices (lists without a directory are searched)
+    SegPlan plan[2];
+    const u64 *tptr[SA_MAX_PHRASE_TERMS];          // current tile: every term's slice
+    u32 tn[SA_MAX_PHRASE_TERMS];
+    const u64 *sptr[PT / 32][SA_MAX_PHRASE_TERMS]; // every warp's chain inputs (compacted candidates, or plain sub-slices)
+    u32 sn[PT / 32][SA_MAX_PHRASE_TERMS];
+    u64 *wfin_docs[PT / 32];
+    u32 wfin_n[PT / 32];
+    u32 ncand, tile_max, work, ok;
+    u32 top[(PT / 32) * 8];
+    __align__(16) float tile[SA_TILE_DOCS];        // bitmaps / compaction buffers first, then the dense tile
+    __align__(8) u64 bar[2];
+};
+
+// warp 0 only: plan the segment that starts at tile `ts` and issue its copies into staging half `h`
+__device__ __forceinline__ void staged_plan(const PhraseArgs &a, const PhraseQuery &pq, StagedShared &P, u64 *stage_half,
+                                            u32 h, u32 ts, u32 tile0, u32 tile1, u64 dend) {
+    const unsigned lane = threadIdx.x & 31;
+    const u32 n_terms = pq.n_terms;
+    SegPlan &pl = P.plan[h];
+    const bool has = lane < n_terms;
+    const bool hd = has && P.has_dir[lane];
+    const u32 base = hd ? P.dirs[lane][ts - tile0] : 0u;
+    const u32 fixed = (has && !hd) ? (u32)min(P.c_n[lane], (u64)0x7FFFFFFFu) : 0u;
+    u32 best = ts + 1;
+    for (u32 cand = ts + 1; cand <= tile1; cand++) {
+        const u32 mine = has ? ((hd ? P.dirs[lane][cand - tile0] - base : fixed) + 4u) : 0u;     // + alignment slack
+        const u32 sum = __reduce_add_sync(0xffffffffu, mine);
+        if (cand > ts + 1 && sum > a.stage_words) break;
+        best = cand;
+        if (sum > a.stage_words) break;
+    }
+    const u32 te = best;
+    // every term's slice of the segment
+    u64 lo = 0;
+    u32 n = 0;
+    if (has) {
+        if (hd) {
+            lo = base;
+            n = P.dirs[lane][te - tile0] - base;
+        } else {                                   // short list without a directory: search its chunk slice
+            const u64 *lst = a.words + pq.off[lane] + P.c_lo[lane];
+            const u64 seg_d0 = a.doc_base + (u64)ts * SA_TILE_DOCS, seg_d1 = min(a.doc_base + (u64)te * SA_TILE_DOCS, dend);
+            u32 l2 = 0, h2 = (u32)P.c_n[lane];
+            while (l2 < h2) { const u32 m = (l2 + h2) >> 1; if ((lst[m] >> SA_KEY_SHIFT) < seg_d0) l2 = m + 1; else h2 = m; }
+            u32 l3 = l2, h3 = (u32)P.c_n[lane];
+            while (l3 < h3) { const u32 m = (l3 + h3) >> 1; if ((lst[m] >> SA_KEY_SHIFT) < seg_d1) l3 = m + 1; else h3 = m; }
+            lo = P.c_lo[lane] + l2;
+            n = l3 - l2;
+        }
+    }
+    // staging layout: terms in order while they fit (exclusive scan over the lanes)
+    const u64 *lst = has ? a.words + pq.off[lane] : nullptr;
+    const u32 wds = (has && n) ? sa_stage_bytes(lst, lo, n) / 8u : 0u;
+    u32 incl = wds;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+    const bool st = wds && incl <= a.stage_words;                 // (a term that does not fit is read from global memory)
+    const u32 so = incl - wds;
+    const u32 total = __reduce_add_sync(0xffffffffu, st ? wds * 8u : 0u);
+    if (lane == 0 && total) {
+        sa_fence_proxy_async();                                  // the half's previous readers are behind a barrier
+        sa_mbar_expect_tx(&P.bar[h], total);
+    }
+    __syncwarp();
+    if (has) {
+        pl.n[lane] = n;
+        pl.dir0[lane] = base;
+        if (st) {
+            const u32 head = sa_stage_issue(stage_half + so, lst, lo, n, &P.bar[h]);
+            pl.ptr[lane] = stage_half + so + head;
+        } else {
+            pl.ptr[lane] = lst + lo;
+        }
+    }
+    if (lane == 0) { pl.te = te; pl.any = total ? 1u : 0u; }
+    __syncwarp();
+}
+
+__device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 chunk, StagedShared &P, u64 *stage,
+                                   u32 (&bar_phase)[2], u64 *cta_slab, const u64 cap) {
+    const PhraseQuery &pq = a.queries[q];
+    const u32 n_terms = pq.n_terms;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 d0 = a.doc_base + (u64)chunk * a.docs_per_chunk;
+    const u64 dend = a.doc_base + a.n_docs;
+    if (d0 >= dend) return;
+    const u64 d1 = min(d0 + a.docs_per_chunk, dend);
+    const u32 tile0 = (u32)(((u64)chunk * a.docs_per_chunk) / SA_TILE_DOCS);
+    const u32 tile1 = (u32)((d1 - a.doc_base + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+    const u32 nt = tile1 - tile0;                                 // <= PS_MAX_CHUNK_TILES (host: sa_phrase_staged_chunks)
     float *out = a.out + (u64)q * a.out_stride;
     Bm25Params p = a.bm25;
     p.idf = pq.idf;
     const u32 row = a.topk_row0 + q;
 
-    u32 ts = tile0;
-    while (ts < tile1) {
-        // ---- the segment [ts, te): the whole chunk (search regime) or as many tiles as the staging buffer holds
-        u32 te = tile1;
-        if (STAGED && run) {
-            if (warp == 0) {
-                const bool has = lane < n_terms;
-                const u32 *dir = (has && pq.dir_plus1[lane] && a.tile_dir) ? a.tile_dir + (pq.dir_plus1[lane] - 1) : nullptr;
-                const u32 fixed = (has && !dir) ? (u32)min(P.n[lane], (u64)0x7FFFFFFFu) : 0u;
-                const u32 base = dir ? __ldg(dir + ts) : 0u;
-                u32 best = ts + 1;
-                for (u32 cand = ts + 1; cand <= tile1; cand++) {
-                    u32 mine = has ? ((dir ? __ldg(dir + cand) - base : fixed) + 4u) : 0u;      // + alignment slack
-                    const u32 sum = __reduce_add_sync(0xffffffffu, mine);
-                    if (cand > ts + 1 && sum > a.stage_words) break;
-                    best = cand;
-                    if (sum > a.stage_words) break;
-                }
-                if (lane == 0) P.seg_te = best;
-            }
-            __syncthreads();
-            te = P.seg_te;
-        }
-        const u64 seg_d0 = a.doc_base + (u64)ts * SA_TILE_DOCS;
-        const u64 seg_d1 = min(a.doc_base + (u64)te * SA_TILE_DOCS, dend);
-        // ---- per-term slices of the segment
-        if (STAGED && run) {
-            for (u32 t = warp; t < n_terms; t += PT / 32) {
-                const u64 *lst = a.words + pq.off[t];
-                u64 lo, hi;
-                if (pq.dir_plus1[t] && a.tile_dir) {
-                    const u32 *dir = a.tile_dir + (pq.dir_plus1[t] - 1);
-                    lo = __ldg(dir + ts);
-                    hi = __ldg(dir + te);
-                } else {
-                    lo = warp_lower_bound_shifted(lst, P.lo[t], P.lo[t] + P.n[t], seg_d0, SA_KEY_SHIFT);
-                    hi = warp_lower_bound_shifted(lst, lo, P.lo[t] + P.n[t], seg_d1, SA_KEY_SHIFT);
-                }
-                if (lane == 0) { P.seg_lo[t] = lo; P.seg_n[t] = hi - lo; }
-            }
-            __syncthreads();
-            // ---- stage: one elected thread arms the barrier and issues one bulk copy per term
-            if (tid == 0) {
-                u32 at = 0, total = 0, seg_ok = 1;
-                bool st[SA_MAX_PHRASE_TERMS];
-                u32 so[SA_MAX_PHRASE_TERMS];
-                for (u32 t = 0; t < n_terms; t++) {
-                    const u32 n = (u32)P.seg_n[t];
-                    const u32 wds = sa_stage_bytes(a.words + pq.off[t], P.seg_lo[t], n) / 8u;
-                    st[t] = n > 0 && P.seg_n[t] < 0x7FFFFFFFull && at + wds <= a.stage_words;
-                    so[t] = at;
-                    if (st[t]) { at += wds; total += wds * 8u; }
-                    if (P.seg_n[t] + 2 > cap) seg_ok = 0;         // cannot happen: the slab is sized from the per-tile maxima
-                }
-                if (total) {
-                    sa_fence_proxy_async();
-                    sa_mbar_expect_tx(&P.bar, total);
-                }
-                for (u32 t = 0; t < n_terms; t++) {
-                    const u64 *lst = a.words + pq.off[t];
-                    if (st[t]) {
-                        const u32 head = sa_stage_issue(stage + so[t], lst, P.seg_lo[t], (u32)P.seg_n[t], &P.bar);
-                        P.ptr[t] = stage + so[t] + head;
-                    } else {
-                        P.ptr[t] = lst + P.seg_lo[t];
-                    }
-                }
-                P.any_staged = total ? 1u : 0u;
-                if (!seg_ok) { P.ok = 0; atomicExch(&a.stats[q].overflow, 1u); }
-            }
-            __syncthreads();
-            if (P.any_staged) {
-                sa_mbar_wait(&P.bar, bar_phase);
-                bar_phase ^= 1u;
-            }
-        } else {
-            if (tid < n_terms) {
-                P.ptr[tid] = a.words + pq.off[tid] + P.lo[tid];
-                P.seg_n[tid] = P.n[tid];
-            }
-            __syncthreads();
-        }
+    // ---- the chunk's directory entries -> shared memory; chunk slices of the lists without a directory
+    __syncthreads();                                              // the previous work item is done with P
+    for (u32 idx = tid; idx < n_terms * (nt + 1); idx += PT) {
+        const u32 t = idx / (nt + 1), j = idx % (nt + 1);
+        const bool hd = pq.dir_plus1[t] && a.tile_dir;
+        P.dirs[t][j] = hd ? __ldg(a.tile_dir + (pq.dir_plus1[t] - 1) + tile0 + j) : 0u;
+        if (j == 0) P.has_dir[t] = hd ? 1u : 0u;
+    }
+    for (u32 t = warp; t < n_terms; t += PT / 32) {
+        if (pq.dir_plus1[t] && a.tile_dir) continue;
+        const u64 *lst = a.words + pq.off[t];
+        const u64 lo = warp_lower_bound_shifted(lst, 0, pq.len[t], d0, SA_KEY_SHIFT);
+        const u64 hi = warp_lower_bound_shifted(lst, lo, pq.len[t], d1, SA_KEY_SHIFT);
+        if (lane == 0) { P.c_lo[t] = lo; P.c_n[t] = hi - lo; }
+    }
+    if (tid == 0) P.ok = 1;
+    __syncthreads();
+    u32 widest = 0;
+    for (u32 t = 0; t < n_terms; t++) {
+        const u64 n = P.has_dir[t] ? (u64)(P.dirs[t][nt] - P.dirs[t][0]) : P.c_n[t];
+        if (n) widest++;
+        if (n + 2 > cap && !P.has_dir[t]) { if (tid == 0) { P.ok = 0; atomicExch(&a.stats[q].overflow, 1u); } }
+    }
+    const bool run = widest >= 2;                                 // fewer than two terms present: no pairs at any step
 
-        if (STAGED) {
-            // ---- merge regime, tile by tile.  A doc can only match if it holds EVERY term of the phrase, so each tile
-            //      first builds one doc-presence bitmap per term from the staged slices (shared-memory atomicOr), ANDs them,
-            //      and only the candidate docs' words (compacted in order, by ballots) enter the bigram chain -- which one
-            //      warp then runs on a few dozen words.  Conjunctions of common terms are rare (df/N of .3, .1, .03, .01:
-            //      9e-6 of the docs), so almost every tile ends at the AND: the lists are streamed once and that is all.
-            //      The pair statistics (same-term speculation) then cover the candidate docs only; sa_phrase.cu's host side
-            //      treats any disagreement with the guess as "re-run exactly" (see sa_phrase_run_sync), which keeps this sound.
-            u32 *cand_bm = reinterpret_cast<u32 *>(P.tile);                      // [256] candidate docs of the tile
-            u32 *term_bm = cand_bm + SA_TILE_DOCS / 32;                           // [n_terms][256], dead once cand_bm exists
-            u64 *fb = reinterpret_cast<u64 *>(cand_bm + SA_TILE_DOCS / 32);       // [n_terms][PW_FB] filtered words (overlays term_bm)
-            for (u32 tile = ts; tile < te; tile++) {
-                const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
-                const u64 td1 = min(td0 + SA_TILE_DOCS, dend);
-                bool have_all = run && P.ok;
-                if (have_all) {
-                    for (u32 t = warp; t < n_terms; t += PT / 32) {
-                        const u64 *base = P.ptr[t];
-                        const u32 n = (u32)P.seg_n[t];
-                        u32 lo = 0, hi = n;
-                        if (te - ts > 1) {
+    if (run && warp == 0) staged_plan(a, pq, P, stage, 0, tile0, tile0, tile1, dend);
+    __syncthreads();
+    const bool ok = P.ok != 0;
+
+    u32 *cand_bm = reinterpret_cast<u32 *>(P.tile);                                   // [256] candidate docs of the tile
+    u32 *term_bm = cand_bm + SA_TILE_DOCS / 32;                                        // [n_terms][256], dead once cand_bm exists
+    u64 *fbw = reinterpret_cast<u64 *>(cand_bm + SA_TILE_DOCS / 32) + (u64)warp * PW_WARP_WORDS;   // this warp's compaction area
+    const u32 fb_cap = PW_WARP_WORDS / n_terms;
+
+    u32 ts = tile0, seg = 0;
+    while (ts < tile1) {
+        const u32 h = seg & 1u;
+        u32 te = tile1;
+        if (run) {
+            te = P.plan[h].te;
+            // prefetch: plan the next segment and issue its copies into the other half before consuming this one
+            if (te < tile1 && warp == 0) staged_plan(a, pq, P, stage + (u64)(h ^ 1u) * a.stage_words, h ^ 1u, te, tile0, tile1, dend);
+            if (P.plan[h].any) {
+                sa_mbar_wait(&P.bar[h], bar_phase[h]);
+                bar_phase[h] ^= 1u;
+            }
+        }
+        const SegPlan &pl = P.plan[h];
+        for (u32 tile = ts; tile < te; tile++) {
+            const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
+            bool have_all = run && ok;
+            if (have_all) {
+                // the tile's slice of every term: directory arithmetic, or a search for the lists without a directory
+                for (u32 t = warp; t < n_terms; t += PT / 32) {
+                    const u64 *base = pl.ptr[t];
+                    const u32 n = pl.n[t];
+                    u32 lo = 0, hi = n;
+                    if (te - ts > 1) {
+                        if (P.has_dir[t]) {
+                            lo = P.dirs[t][tile - tile0] - pl.dir0[t];
+                            hi = P.dirs[t][tile + 1 - tile0] - pl.dir0[t];
+                        } else {
                             lo = w_lower_bound_doc(base, n, td0);
-                            hi = lo + w_lower_bound_doc(base + lo, n - lo, td1);
+                            hi = lo + w_lower_bound_doc(base + lo, n - lo, td0 + SA_TILE_DOCS);
                         }
-                        if (lane == 0) { P.wptr[0][t] = base + lo; P.wn[0][t] = hi - lo; }
                     }
-                    __syncthreads();
-                    for (u32 t = 0; t < n_terms; t++) have_all = have_all && P.wn[0][t] > 0;
+                    if (lane == 0) { P.tptr[t] = base + lo; P.tn[t] = hi - lo; }
                 }
-                u32 n_cand = 0;
-                bool filtered = false;
-                if (have_all) {                                                  // CTA-uniform
-                    for (u32 i = tid; i < n_terms * (SA_TILE_DOCS / 32); i += PT) term_bm[i] = 0u;
-                    if (tid == 0) P.ncand = 0;
-                    __syncthreads();
-                    for (u32 t = 0; t < n_terms; t++) {
-                        const u64 *lst = P.wptr[0][t];
-                        const u32 n = P.wn[0][t];
-                        u32 *bm = term_bm + t * (SA_TILE_DOCS / 32);
-                        for (u32 i = tid; i < n; i += PT) {
-                            const u32 rel = (u32)((lst[i] >> SA_KEY_SHIFT) - td0);
-                            atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
-                        }
-                    }
-                    __syncthreads();
-                    {
-                        u32 c = term_bm[tid];
-                        for (u32 t = 1; t < n_terms; t++) c &= term_bm[t * (SA_TILE_DOCS / 32) + tid];
-                        const u32 cnt = __reduce_add_sync(0xffffffffu, (u32)__popc(c));
-                        if (lane == 0 && cnt) atomicAdd(&P.ncand, cnt);
-                        __syncthreads();                                         // every term_bm word is read before cand_bm / fb overwrite the region
-                        cand_bm[tid] = c;
-                    }
-                    __syncthreads();
-                    n_cand = P.ncand;
-                    if (n_cand) {
-                        // ordered compaction of the candidate docs' words, one warp per term
-                        for (u32 t = warp; t < n_terms; t += PT / 32) {
-                            const u64 *lst = P.wptr[0][t];
-                            const u32 n = P.wn[0][t];
-                            u64 *dst = fb + (u64)t * PW_FB;
-                            u32 cnt = 0;
-                            for (u32 i0 = 0; i0 < n; i0 += 32) {
-                                const u32 i = i0 + lane;
-                                u64 w = 0;
-                                bool keep = false;
-                                if (i < n) {
-                                    w = lst[i];
-                                    const u32 rel = (u32)((w >> SA_KEY_SHIFT) - td0);
-                                    keep = (cand_bm[rel >> 5] >> (rel & 31u)) & 1u;
-                                }
-                                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                                const u32 at = cnt + __popc(m & ((1u << lane) - 1u));
-                                if (keep && at < PW_FB) dst[at] = w;
-                                cnt += __popc(m);
-                            }
-                            if (lane == 0) P.wn[1][t] = cnt;
-                        }
-                        __syncthreads();
-                        filtered = true;
-                        for (u32 t = 0; t < n_terms; t++) filtered = filtered && P.wn[1][t] <= PW_FB;
+                __syncthreads();
+                for (u32 t = 0; t < n_terms; t++) have_all = have_all && P.tn[t] > 0;
+            }
+            u32 n_cand = 0;
+            if (have_all) {                                                           // CTA-uniform
+                for (u32 i = tid; i < n_terms * (SA_TILE_DOCS / 32); i += PT) term_bm[i] = 0u;
+                if (tid == 0) P.ncand = 0;
+                __syncthreads();
+                for (u32 t = 0; t < n_terms; t++) {
+                    const u64 *lst = P.tptr[t];
+                    const u32 n = P.tn[t];
+                    u32 *bm = term_bm + t * (SA_TILE_DOCS / 32);
+                    for (u32 i = tid; i < n; i += PT) {
+                        const u32 rel = (u32)((lst[i] >> SA_KEY_SHIFT) - td0);
+                        atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
                     }
                 }
-                // ---- the chain
-                if (n_cand && filtered) {
-                    if (warp == 0) {                                             // a few dozen words: one warp
-                        if (lane < n_terms) { P.wptr[1][lane] = fb + (u64)lane * PW_FB; }
-                        __syncwarp();
-                        const WarpFin wf = warp_phrase_chain(pq, P.wptr[1], P.wn[1], cta_slab, cap, &a.stats[q]);
-                        if (lane == 0) { P.wfin_docs[0] = wf.docs; P.wfin_n[0] = wf.n_docs; }
-                    } else if (lane == 0) {
-                        P.wfin_docs[warp] = nullptr;
-                        P.wfin_n[warp] = 0;
-                    }
-                } else if (n_cand) {
-                    // too many candidates to compact (dense conjunctions): eight warps, eight doc sub-ranges of the tile
-                    const u64 t_docs = td1 - td0;
-                    const u64 w_d0 = td0 + t_docs * warp / (PT / 32), w_d1 = td0 + t_docs * (warp + 1) / (PT / 32);
+                __syncthreads();
+                u32 c = term_bm[tid];
+                for (u32 t = 1; t < n_terms; t++) c &= term_bm[t * (SA_TILE_DOCS / 32) + tid];
+                const u32 cnt = __reduce_add_sync(0xffffffffu, (u32)__popc(c));
+                if (lane == 0 && cnt) atomicAdd(&P.ncand, cnt);
+                __syncthreads();                                  // every term_bm word is read before the region is reused
+                cand_bm[tid] = c;
+                __syncthreads();
+                n_cand = P.ncand;
+            }
+            // ---- candidates: each warp takes 1,024 docs of the tile
+            WarpFin wf;
+            wf.docs = nullptr;
+            wf.n_docs = 0;
+            if (n_cand) {
+                const u32 cw = cand_bm[warp * 32 + lane];
+                if (__reduce_add_sync(0xffffffffu, (u32)__popc(cw))) {                // warp-uniform
+                    const u64 w_d0 = td0 + (u64)warp * (SA_TILE_DOCS / (PT / 32)), w_d1 = w_d0 + SA_TILE_DOCS / (PT / 32);
                     for (u32 t = 0; t < n_terms; t++) {
-                        const u64 *base = P.wptr[0][t];
-                        const u32 n = P.wn[0][t];
+                        const u64 *base = P.tptr[t];
+                        const u32 n = P.tn[t];
                         const u32 lo = w_lower_bound_doc(base, n, w_d0);
                         const u32 hi = lo + w_lower_bound_doc(base + lo, n - lo, w_d1);
-                        if (lane == 0) { P.sptr[warp][t] = base + lo; P.sn[warp][t] = hi - lo; }
+                        u64 *dst = fbw + (u64)t * fb_cap;
+                        u32 kept = 0;
+                        for (u32 i0 = lo; i0 < hi; i0 += 32) {                         // ordered compaction by ballots
+                            const u32 i = i0 + lane;
+                            u64 w = 0;
+                            bool keep = false;
+                            if (i < hi) {
+                                w = base[i];
+                                const u32 rel = (u32)((w >> SA_KEY_SHIFT) - td0);
+                                keep = (cand_bm[rel >> 5] >> (rel & 31u)) & 1u;
+                            }
+                            const unsigned m = __ballot_sync(0xffffffffu, keep);
+                            const u32 at = kept + __popc(m & ((1u << lane) - 1u));
+                            if (keep && at < fb_cap) dst[at] = w;
+                            kept += __popc(m);
+                        }
+                        if (lane == 0) {
+                            // (a list too long to compact enters the chain whole: its extra docs die at the other terms)
+                            P.sptr[warp][t] = kept <= fb_cap ? dst : base + lo;
+                            P.sn[warp][t] = kept <= fb_cap ? kept : hi - lo;
+                        }
                     }
                     __syncwarp();
-                    const WarpFin wf = warp_phrase_chain(pq, P.sptr[warp], P.sn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
-                    if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
-                } else if (lane == 0) {
-                    P.wfin_docs[warp] = nullptr;
-                    P.wfin_n[warp] = 0;
+                    wf = warp_phrase_chain(pq, P.sptr[warp], P.sn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
                 }
-                __syncthreads();
-                // ---- materialise the tile: every warp scatters its own (sorted) result list
-                const u64 *wl = P.wfin_docs[warp];
-                const u32 wln = P.wfin_n[warp];
-                u32 total = 0;
+            }
+            if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
+            __syncthreads();
+            // ---- materialise the tile: every warp scatters its own (sorted) result list
+            u32 total = 0, holders = 0;
 #pragma unroll
-                for (int w = 0; w < PT / 32; w++) total += P.wfin_n[w];
-                if (total == 0) {
-                    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int w = 0; w < PT / 32; w++) { total += P.wfin_n[w]; holders += min(P.wfin_n[w], 32u); }
+            if (total == 0) {
+                float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
-                    if (a.topk.k && tid == 0) {
-                        const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
-                        a.topk.tile_cnt[t_idx] = 0;
-                        a.topk.tile_max[t_idx] = 0;
-                    }
-                    __syncthreads();                        // the per-warp result slots are rewritten for the next tile
-                    continue;
+                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+                if (a.topk.k && tid == 0) {
+                    const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                    a.topk.tile_cnt[t_idx] = 0;
+                    a.topk.tile_max[t_idx] = 0;
                 }
+                __syncthreads();                                  // the per-warp result slots are rewritten for the next tile
+                continue;
+            }
 #pragma unroll
-                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
-                    reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-                u32 my_max = 0, my_match = 0;
-                for (u32 i = lane; i < wln; i += 32) {
-                    const u64 e = wl[i];
-                    const u32 c = (u32)(e & 0xFFFFFFFFull);
-                    if (c == 0) continue;
-                    const u64 d = (e >> 32) - a.doc_base;
-                    if (d >= a.n_docs) continue;
-                    my_match++;
-                    const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
-                    P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
-                    if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
-                }
-                my_match = __reduce_add_sync(0xffffffffu, my_match);
-                if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
-                __syncthreads();
-                flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, total,
-                                   P.top, &P.ncand, &P.tile_max);
+            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
+                reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            u32 my_max = 0, my_match = 0;
+            for (u32 i = lane; i < wf.n_docs; i += 32) {
+                const u64 e = wf.docs[i];
+                const u32 c = (u32)(e & 0xFFFFFFFFull);
+                if (c == 0) continue;
+                const u64 d = (e >> 32) - a.doc_base;
+                if (d >= a.n_docs) continue;
+                my_match++;
+                const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
+                P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
+                if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
             }
-        } else {
-        ChainResult fin;
-            fin.docs = nullptr; fin.n_docs = 0; fin.cont = nullptr; fin.n_cont = 0;
-            if (run && P.ok) {
-                if (pq.mode == SA_PHRASE_MODE_LR) {
-                    fin = run_chain(0, n_terms, true, docsL);
-                } else if (pq.mode == SA_PHRASE_MODE_RL) {
-                    fin = run_chain(0, n_terms, false, docsL);
-                } else {
-                    // both chains always run (their pair statistics feed the speculation check)
-                    ChainResult left = run_chain(0, pq.split, true, docsL);
-                    fin = run_chain(pq.split, n_terms, false, docsR);
-                    if (left.n_docs == 0) fin.n_docs = 0;
-                    and_min(fin.docs, fin.n_docs, left.docs, left.n_docs);
-                }
-            }
-            // optional dump for the per-op parity export (single chunk, search regime)
-            if (!STAGED && a.dump.cont) {
-                for (u64 i = tid; i < fin.n_cont; i += PT) a.dump.cont[i] = fin.cont[i];
-                for (u64 i = tid; i < fin.n_docs; i += PT) a.dump.docs[i] = fin.docs[i];
-                if (tid == 0) { *a.dump.n_cont = fin.n_cont; *a.dump.n_docs = fin.n_docs; }
-            }
-    
-            // 3. materialise the dense vector of the segment tile by tile (phrase_freqs[ids] = counts,
-            //    middle_out.py:441): zeros + the matches that fall in the tile, flushed with 16-byte
-            //    streaming stores; the same pass collects the tile's top-k candidates.
-            // fin.docs is sorted by doc and the tiles ascend: a running cursor replaces a search per tile.
-            // Most tiles hold no match at all: they are written as zeros straight from registers (no shared
-            // tile, no barrier), so the bulk of the 4*N write runs at fill speed.
-            u64 cur = 0;
-            u64 next_doc = fin.n_docs ? (fin.docs[0] >> 32) : ~0ull;          // CTA-uniform
-            for (u32 tile = ts; tile < te; tile++) {
-                const u64 t_abs1 = a.doc_base + (u64)tile * SA_TILE_DOCS + SA_TILE_DOCS;
-                if (next_doc >= t_abs1) {
-                    float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    #pragma unroll
-                    for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
-                    if (a.topk.k && tid == 0) {
-                        const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
-                        a.topk.tile_cnt[t_idx] = 0;
-                        a.topk.tile_max[t_idx] = 0;
-                    }
-                    continue;
-                }
-                // first entry at or past the end of this tile: gallop from the cursor, then bisect (uniform)
-                const u64 m0 = cur;
-                u64 lo = cur + 1, hi = fin.n_docs, st = 1;
-                while (lo < hi) {
-                    const u64 probe = min(lo + st - 1, hi - 1);
-                    if ((fin.docs[probe] >> 32) < t_abs1) { lo = probe + 1; st <<= 1; }
-                    else { hi = probe; break; }
-                }
-                while (lo < hi) {
-                    const u64 mid = (lo + hi) >> 1;
-                    if ((fin.docs[mid] >> 32) < t_abs1) lo = mid + 1; else hi = mid;
-                }
-                const u64 m1 = lo;
-                cur = m1;
-                next_doc = m1 < fin.n_docs ? (fin.docs[m1] >> 32) : ~0ull;
-    #pragma unroll
-                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
-                    reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-                u32 my_max = 0, my_match = 0;
-                for (u64 i = m0 + tid; i < m1; i += PT) {
-                    const u64 e = fin.docs[i];
-                    const u32 c = (u32)(e & 0xFFFFFFFFull);
-                    if (c == 0) continue;
-                    const u64 d = (e >> 32) - a.doc_base;
-                    if (d >= a.n_docs) continue;
-                    my_match++;
-                    const float v = a.score ? bm25_one((float)c, __ldg(a.doc_lens + d), p) : (float)c;
-                    P.tile[d - (u64)tile * SA_TILE_DOCS] = v;
-                    if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
-                }
-                my_match = __reduce_add_sync(0xffffffffu, my_match);
-                if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
-                __syncthreads();
-                flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, (u32)(m1 - m0),
-                                   P.top, &P.ncand, &P.tile_max);
-            }
+            my_match = __reduce_add_sync(0xffffffffu, my_match);
+            if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
+            __syncthreads();
+            flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, total, holders,
+                               P.top, &P.ncand, &P.tile_max);
         }
-        __syncthreads();                    // every read of the staged slices / the slab is done before the next segment
+        __syncthreads();                    // every read of this half of the staging buffer is done: it may be refilled
         ts = te;
+        seg++;
     }
-}
-
-__global__ void __launch_bounds__(PT, 4)
-phrase_kernel(const PhraseArgs a) {
-    __shared__ PhraseShared P;
-    // grid = (queries, chunks): neighbouring CTAs belong to different queries (see term_tile_kernel)
-    u32 phase = 0;
-    const u32 q = a.qsel ? a.qsel[blockIdx.x] : blockIdx.x;
-    phrase_work<false>(a, q, blockIdx.y, P, nullptr, phase, nullptr, 0);
 }
 
 // Persistent CTAs (grid = resident CTAs of the device): work items (query, chunk) are claimed with an atomic
-// counter, each CTA keeps its staging buffer (dynamic shared memory), its mbarrier and its scratch slab.
-__global__ void __launch_bounds__(PT)
+// counter, each CTA keeps its staging buffer (dynamic shared memory, two halves), its mbarriers and its scratch slab.
+__global__ void __launch_bounds__(PT, 2)
 phrase_staged_kernel(const PhraseArgs a) {
-    __shared__ PhraseShared P;
+    __shared__ StagedShared P;
     extern __shared__ __align__(16) u64 s_stage[];
     if (threadIdx.x == 0) {
-        sa_mbar_init(&P.bar, 1);
+        sa_mbar_init(&P.bar[0], 1);
+        sa_mbar_init(&P.bar[1], 1);
         sa_mbar_fence_init();
     }
     __syncthreads();
-    u32 phase = 0;
+    u32 phase[2] = {0u, 0u};
     u64 *slab = a.slabs + (u64)blockIdx.x * (PT / 32) * 6ull * a.slab_cap;      // six buffers for each of the CTA's warps
     const u32 n_work = a.n_sel * a.n_chunks;
     for (;;) {
@@ -831,7 +864,7 @@ phrase_staged_kernel(const PhraseArgs a) {
         if (w >= n_work) break;
         // consecutive work items belong to different queries (dense and sparse lists interleave on an SM)
         const u32 q = a.qsel[w % a.n_sel], chunk = w / a.n_sel;
-        phrase_work<true>(a, q, chunk, P, s_stage, phase, slab, a.slab_cap);
+        phrase_work_staged(a, q, chunk, P, s_stage, phase, slab, a.slab_cap);
     }
 }
 
@@ -850,7 +883,7 @@ int launch_phrase(sa_index *ix, const PhraseArgs &a, u32 n_queries) {
 // resident CTAs of phrase_staged_kernel with `stage_words` words of dynamic shared memory
 static int staged_grid(sa_index *ix, u32 stage_words, u32 *ctas_out) {
     static bool attr_set = false;
-    const size_t dyn = (size_t)stage_words * sizeof(u64);
+    const size_t dyn = 2 * (size_t)stage_words * sizeof(u64);            // two halves (double buffering)
     if (!attr_set) {
         SA_CUDA(cudaFuncSetAttribute(phrase_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
@@ -864,7 +897,7 @@ static int staged_grid(sa_index *ix, u32 stage_words, u32 *ctas_out) {
 
 u32 sa_phrase_stage_words() {
     static const long env = getenv("SA_PHRASE_STAGE_WORDS") ? atol(getenv("SA_PHRASE_STAGE_WORDS")) : 0;
-    return env > 0 ? (u32)std::min<long>(env, 18 * 1024) : 8192u;
+    return env > 0 ? (u32)std::min<long>(env, 9 * 1024) : 4608u;        // per half; 2 x 36 KB + 38 KB static: two CTAs per SM
 }
 
 // Merge regime or search regime?  Staging reads every list once (8 * sum(W) bytes); the search path costs about
@@ -1124,7 +1157,7 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
     a.work_counter = (u32 *)(d_arena_used + 1);                 // zeroed with the arena counter
     const u64 n_work = (u64)a.n_sel * a.n_chunks;
     KernelTimer t(ix, 2);
-    phrase_staged_kernel<<<(unsigned)std::min<u64>(ctas, n_work), PT, (size_t)stage_words * sizeof(u64), ix->stream>>>(a);
+    phrase_staged_kernel<<<(unsigned)std::min<u64>(ctas, n_work), PT, 2 * (size_t)stage_words * sizeof(u64), ix->stream>>>(a);
     SA_CUDA(cudaGetLastError());
     t.stop();
     ix->stats.phrase_kernel_launches++;

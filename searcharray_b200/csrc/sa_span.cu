@@ -793,7 +793,7 @@ span_tiles_kernel(const SpanArgs a) {
             }
         }
         __syncthreads();
-        flush_tile_collect(s_tile, out + t0, a.topk, row, tile, my_max, n_items, s_top, &s_ncand, &s_tile_max);
+        flush_tile_collect(s_tile, out + t0, a.topk, row, tile, my_max, n_items, min(n_items, (u32)SA_TERM_THREADS), s_top, &s_ncand, &s_tile_max);
     }
 }
 

@@ -277,7 +277,8 @@ term_tile_kernel(const TermBatchArgs a) {
     //    derives the same tile bound; scores >= bound are this tile's candidates.
     const u32 k = a.topk.k;
     const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
-    const u32 M = tile_bound_width(k, hi - lo);
+    // threads that can hold a score: one per record / posting word, or one per quad of records on the dense tf-table path
+    const u32 M = tile_bound_width(k, (use_recs && hi - lo >= 128u) ? (hi - lo) / 4u : (hi - lo));
     if (need_bound) {
         u32 v = my_max;
         for (u32 r = 0; r < M; r++) {

@@ -172,20 +172,21 @@ __device__ __forceinline__ void tile_collect_ties_retry(const float *s_out, bool
 // How many of its largest thread maxima every warp publishes for the tile bound.  4 per warp are enough for k <= 10
 // when all eight warps hold scores; a tile whose scores sit in two or three warps (a few dozen docs) must publish 8 per
 // warp, or fewer than k values exist, the bound degenerates to "keep everything" and 65+ docs overflow the 64 slots.
-__device__ __forceinline__ u32 tile_bound_width(u32 k, u32 n_items) { return (k <= 10 && n_items >= SA_TERM_THREADS) ? 4u : 8u; }
+// `n_holders`: how many threads can hold a score (not how many scores there are).
+__device__ __forceinline__ u32 tile_bound_width(u32 k, u32 n_holders) { return (k <= 10 && n_holders >= SA_TERM_THREADS) ? 4u : 8u; }
 
 // Flush one shared-memory score tile to its dense row with 16-byte streaming stores and, on the way,
 // collect the tile's top-k candidates (private slots, count, maximum): the same step the term kernel
 // ends with, shared with the phrase kernel.  `my_max` = largest score bits this thread put into the
-// tile, `n_items` = number of scores in the tile.  All SA_TERM_THREADS threads must call.
+// tile, `n_items` = number of scores in the tile, `n_holders` = how many threads can hold one of them.  All SA_TERM_THREADS threads must call.
 __device__ __forceinline__ void flush_tile_collect(const float *s_out, float *__restrict__ out_tile, const TopkCtx &t,
-                                                   u32 row, u32 tile, u32 my_max, u32 n_items, u32 *s_top,
+                                                   u32 row, u32 tile, u32 my_max, u32 n_items, u32 n_holders, u32 *s_top,
                                                    u32 *s_ncand, u32 *s_tile_max) {
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const u32 k = t.k;
     const u32 tile_doc0 = tile * SA_TILE_DOCS;
     const bool need_bound = k && n_items > k;                        // CTA-uniform
-    const u32 M = tile_bound_width(k, n_items);
+    const u32 M = tile_bound_width(k, n_holders);
     if (need_bound) {
         u32 v = my_max;
         for (u32 r = 0; r < M; r++) {
