@@ -35,7 +35,7 @@ int sa_filter_terms(sa_index *ix, const uint32_t *term_ids, uint32_t n_terms, bo
 int sa_gather_rows(sa_index *ix, const float *d_dense, float *out_host);
 
 #define PT SA_PHRASE_THREADS
-#define PW_WARP_WORDS 496 // words of compaction area per warp in the merge regime ((32 KB tile - 1 KB candidate bitmap) / 8 warps)
+#define PW_SUB_DOCS (SA_TILE_DOCS / (SA_PHRASE_THREADS / 32))   // docs of a tile that one warp of the merge regime owns (1,024)
 
 static u64 docs_per_chunk_of(const sa_index *ix, u32 n_chunks);
 
@@ -566,12 +566,9 @@ struct StagedShared {
     u32 has_dir[SA_MAX_PHRASE_TERMS];
     u64 c_lo[SA_MAX_PHRASE_TERMS], c_n[SA_MAX_PHRASE_TERMS];  // chunk slices (lists without a directory are searched)
     SegPlan plan[2];
-    const u64 *tptr[SA_MAX_PHRASE_TERMS];          // current tile: every term's slice
-    u32 tn[SA_MAX_PHRASE_TERMS];
     const u64 *sptr[PT / 32][SA_MAX_PHRASE_TERMS]; // every warp's chain inputs (compacted candidates, or plain sub-slices)
     u32 sn[PT / 32][SA_MAX_PHRASE_TERMS];
-    u64 *wfin_docs[PT / 32];
-    u32 wfin_n[PT / 32];
+    u32 wmatch[2][PT / 32];                        // matches of every warp, alternating between consecutive tiles
     u32 ncand, tile_max, work, ok;
     u32 top[(PT / 32) * 8];
     __align__(16) float tile[SA_TILE_DOCS];        // bitmaps / compaction buffers first, then the dense tile
@@ -689,12 +686,7 @@ __device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 c
     __syncthreads();
     const bool ok = P.ok != 0;
 
-    u32 *cand_bm = reinterpret_cast<u32 *>(P.tile);                                   // [256] candidate docs of the tile
-    u32 *term_bm = cand_bm + SA_TILE_DOCS / 32;                                        // [n_terms][256], dead once cand_bm exists
-    u64 *fbw = reinterpret_cast<u64 *>(cand_bm + SA_TILE_DOCS / 32) + (u64)warp * PW_WARP_WORDS;   // this warp's compaction area
-    const u32 fb_cap = PW_WARP_WORDS / n_terms;
-
-    u32 ts = tile0, seg = 0;
+    u32 ts = tile0, seg = 0, tile_no = 0;
     while (ts < tile1) {
         const u32 h = seg & 1u;
         u32 te = tile1;
@@ -708,76 +700,85 @@ __device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 c
             }
         }
         const SegPlan &pl = P.plan[h];
-        for (u32 tile = ts; tile < te; tile++) {
+        for (u32 tile = ts; tile < te; tile++, tile_no++) {
+            // ---- every warp takes 1,024 docs of the tile and works on them WITHOUT block barriers: sub-slice bounds
+            //      (lane-parallel binary searches), doc-presence bitmaps of the terms (one 32-bit word per lane), their
+            //      AND, ordered compaction of the candidate docs' words, the bigram chain, and its 4 KB of the dense tile.
+            //      The warp's scratch overlays its own slice of the tile.
             const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
-            bool have_all = run && ok;
-            if (have_all) {
-                // the tile's slice of every term: directory arithmetic, or a search for the lists without a directory
-                for (u32 t = warp; t < n_terms; t += PT / 32) {
-                    const u64 *base = pl.ptr[t];
-                    const u32 n = pl.n[t];
+            const u64 w_d0 = td0 + (u64)warp * PW_SUB_DOCS, w_d1 = w_d0 + PW_SUB_DOCS;
+            float *my_slice = P.tile + warp * PW_SUB_DOCS;
+            u32 *wbm = reinterpret_cast<u32 *>(my_slice);                       // [n_terms][32] presence bitmaps
+            u32 *wcand = wbm + n_terms * 32;                                    // [32] candidate docs
+            u64 *fbw = reinterpret_cast<u64 *>(wcand + 32);                     // compaction area
+            const u32 fb_cap = ((PW_SUB_DOCS * 4 - (n_terms + 1) * 128) / 8) / n_terms;
+            WarpFin wf;
+            wf.docs = nullptr;
+            wf.n_docs = 0;
+            if (run && ok) {
+                // the tile's slice of term `lane`
+                const u64 *t_ptr = nullptr;
+                u32 t_n = 0;
+                if (lane < n_terms) {
+                    const u64 *base = pl.ptr[lane];
+                    const u32 n = pl.n[lane];
                     u32 lo = 0, hi = n;
                     if (te - ts > 1) {
-                        if (P.has_dir[t]) {
-                            lo = P.dirs[t][tile - tile0] - pl.dir0[t];
-                            hi = P.dirs[t][tile + 1 - tile0] - pl.dir0[t];
+                        if (P.has_dir[lane]) {
+                            lo = P.dirs[lane][tile - tile0] - pl.dir0[lane];
+                            hi = P.dirs[lane][tile + 1 - tile0] - pl.dir0[lane];
                         } else {
                             lo = w_lower_bound_doc(base, n, td0);
                             hi = lo + w_lower_bound_doc(base + lo, n - lo, td0 + SA_TILE_DOCS);
                         }
                     }
-                    if (lane == 0) { P.tptr[t] = base + lo; P.tn[t] = hi - lo; }
+                    t_ptr = base + lo;
+                    t_n = hi - lo;
                 }
-                __syncthreads();
-                for (u32 t = 0; t < n_terms; t++) have_all = have_all && P.tn[t] > 0;
-            }
-            u32 n_cand = 0;
-            if (have_all) {                                                           // CTA-uniform
-                for (u32 i = tid; i < n_terms * (SA_TILE_DOCS / 32); i += PT) term_bm[i] = 0u;
-                if (tid == 0) P.ncand = 0;
-                __syncthreads();
+                // this warp's sub-slice bounds: lane 2t searches the lower, lane 2t+1 the upper doc bound of term t
+                u32 bound = 0;
+                {
+                    const u32 t = lane >> 1;
+                    const u64 ptr_bits = __shfl_sync(0xffffffffu, (u64)(uintptr_t)t_ptr, t);
+                    const u32 n = __shfl_sync(0xffffffffu, t_n, t);
+                    if (t < n_terms) bound = w_lower_bound_doc(reinterpret_cast<const u64 *>((uintptr_t)ptr_bits), n, (lane & 1u) ? w_d1 : w_d0);
+                }
+                bool all_present = true;
+                for (u32 t = 0; t < n_terms; t++) wbm[t * 32 + lane] = 0u;
+                __syncwarp();
                 for (u32 t = 0; t < n_terms; t++) {
-                    const u64 *lst = P.tptr[t];
-                    const u32 n = P.tn[t];
-                    u32 *bm = term_bm + t * (SA_TILE_DOCS / 32);
-                    for (u32 i = tid; i < n; i += PT) {
-                        const u32 rel = (u32)((lst[i] >> SA_KEY_SHIFT) - td0);
+                    const u64 *base = reinterpret_cast<const u64 *>((uintptr_t)__shfl_sync(0xffffffffu, (u64)(uintptr_t)t_ptr, t));
+                    const u32 lo = __shfl_sync(0xffffffffu, bound, 2 * t), hi = __shfl_sync(0xffffffffu, bound, 2 * t + 1);
+                    all_present = all_present && hi > lo;
+                    if (!all_present) break;                                    // warp-uniform
+                    u32 *bm = wbm + t * 32;
+                    for (u32 i = lo + lane; i < hi; i += 32) {
+                        const u32 rel = (u32)((base[i] >> SA_KEY_SHIFT) - w_d0);
                         atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
                     }
                 }
-                __syncthreads();
-                u32 c = term_bm[tid];
-                for (u32 t = 1; t < n_terms; t++) c &= term_bm[t * (SA_TILE_DOCS / 32) + tid];
-                const u32 cnt = __reduce_add_sync(0xffffffffu, (u32)__popc(c));
-                if (lane == 0 && cnt) atomicAdd(&P.ncand, cnt);
-                __syncthreads();                                  // every term_bm word is read before the region is reused
-                cand_bm[tid] = c;
-                __syncthreads();
-                n_cand = P.ncand;
-            }
-            // ---- candidates: each warp takes 1,024 docs of the tile
-            WarpFin wf;
-            wf.docs = nullptr;
-            wf.n_docs = 0;
-            if (n_cand) {
-                const u32 cw = cand_bm[warp * 32 + lane];
-                if (__reduce_add_sync(0xffffffffu, (u32)__popc(cw))) {                // warp-uniform
-                    const u64 w_d0 = td0 + (u64)warp * (SA_TILE_DOCS / (PT / 32)), w_d1 = w_d0 + SA_TILE_DOCS / (PT / 32);
+                __syncwarp();
+                u32 c = 0;
+                if (all_present) {
+                    c = wbm[lane];
+                    for (u32 t = 1; t < n_terms; t++) c &= wbm[t * 32 + lane];
+                }
+                if (__reduce_add_sync(0xffffffffu, (u32)__popc(c))) {          // warp-uniform: candidates in this sub-range
+                    wcand[lane] = c;
+                    __syncwarp();
                     for (u32 t = 0; t < n_terms; t++) {
-                        const u64 *base = P.tptr[t];
-                        const u32 n = P.tn[t];
-                        const u32 lo = w_lower_bound_doc(base, n, w_d0);
-                        const u32 hi = lo + w_lower_bound_doc(base + lo, n - lo, w_d1);
+                        const u64 *base = reinterpret_cast<const u64 *>((uintptr_t)__shfl_sync(0xffffffffu, (u64)(uintptr_t)t_ptr, t));
+                        const u32 lo = __shfl_sync(0xffffffffu, bound, 2 * t), hi = __shfl_sync(0xffffffffu, bound, 2 * t + 1);
                         u64 *dst = fbw + (u64)t * fb_cap;
                         u32 kept = 0;
-                        for (u32 i0 = lo; i0 < hi; i0 += 32) {                         // ordered compaction by ballots
+                        for (u32 i0 = lo; i0 < hi; i0 += 32) {                 // ordered compaction by ballots
                             const u32 i = i0 + lane;
                             u64 w = 0;
                             bool keep = false;
                             if (i < hi) {
                                 w = base[i];
-                                const u32 rel = (u32)((w >> SA_KEY_SHIFT) - td0);
-                                keep = (cand_bm[rel >> 5] >> (rel & 31u)) & 1u;
+                                const u32 rel = (u32)((w >> SA_KEY_SHIFT) - w_d0);
+                                keep = (wcand[rel >> 5] >> (rel & 31u)) & 1u;
                             }
                             const unsigned m = __ballot_sync(0xffffffffu, keep);
                             const u32 at = kept + __popc(m & ((1u << lane) - 1u));
@@ -794,29 +795,12 @@ __device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 c
                     wf = warp_phrase_chain(pq, P.sptr[warp], P.sn[warp], cta_slab + (u64)warp * 6ull * cap, cap, &a.stats[q]);
                 }
             }
-            if (lane == 0) { P.wfin_docs[warp] = wf.docs; P.wfin_n[warp] = wf.n_docs; }
-            __syncthreads();
-            // ---- materialise the tile: every warp scatters its own (sorted) result list
-            u32 total = 0, holders = 0;
+            // ---- this warp's 4 KB of the dense tile: zeros + its matches
+            __syncwarp();
 #pragma unroll
-            for (int w = 0; w < PT / 32; w++) { total += P.wfin_n[w]; holders += min(P.wfin_n[w], 32u); }
-            if (total == 0) {
-                float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
-                if (a.topk.k && tid == 0) {
-                    const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
-                    a.topk.tile_cnt[t_idx] = 0;
-                    a.topk.tile_max[t_idx] = 0;
-                }
-                __syncthreads();                                  // the per-warp result slots are rewritten for the next tile
-                continue;
-            }
-#pragma unroll
-            for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++)
-                reinterpret_cast<float4 *>(P.tile)[tid + i * PT] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
+            for (int i = 0; i < PW_SUB_DOCS / 32 / 4; i++)
+                reinterpret_cast<float4 *>(my_slice)[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
             u32 my_max = 0, my_match = 0;
             for (u32 i = lane; i < wf.n_docs; i += 32) {
                 const u64 e = wf.docs[i];
@@ -830,8 +814,26 @@ __device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 c
                 if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
             }
             my_match = __reduce_add_sync(0xffffffffu, my_match);
-            if (lane == 0 && my_match) atomicAdd(&a.stats[q].n_match, my_match);
-            __syncthreads();
+            if (lane == 0) {
+                if (my_match) atomicAdd(&a.stats[q].n_match, my_match);
+                P.wmatch[tile_no & 1u][warp] = my_match;
+            }
+            __syncthreads();                                                  // the tile's only block barrier (besides the flush's own)
+            u32 total = 0, holders = 0;
+#pragma unroll
+            for (int w = 0; w < PT / 32; w++) { const u32 m = P.wmatch[tile_no & 1u][w]; total += m; holders += min(m, 32u); }
+            if (total == 0) {
+                float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+                if (a.topk.k && tid == 0) {
+                    const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+                    a.topk.tile_cnt[t_idx] = 0;
+                    a.topk.tile_max[t_idx] = 0;
+                }
+                continue;                                                      // (the next tile's scratch lives in the warps' own slices)
+            }
             flush_tile_collect(P.tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, total, holders,
                                P.top, &P.ncand, &P.tile_max);
         }
