@@ -846,7 +846,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
                     else for (u32 i = 0; i < nt; i++)
                         if (ix->h_dir_off[tids[i]] != SA_NO_DIR) pq.dir_plus1[i] = ix->h_dir_off[tids[i]] + 1;
                     sa_phrase_plan(pq, tids);
-                    if (!missing && sa_phrase_is_staged(pq)) {
+                    if (!missing && sa_phrase_is_staged(pq, ix->n_docs)) {
                         pq.pad = 1;                                               // merge regime (see below)
                         C.slab_cap = std::max(C.slab_cap, sa_phrase_slab_cap(ix, tids, nt));
                     }
@@ -1089,9 +1089,9 @@ int sa_batch_fix_overflow_locked(sa_index *ix, u32 *n_redone) {
         }
         for (u32 i = 0; i < C.n_phrase; i++) {
             const u32 pi = C.phrase0 + i;
-            SA_CHECK(!st[pi].overflow, "phrase scratch arena exhausted (internal sizing error)");
+            SA_CHECK(st[pi].overflow != 1, "phrase scratch arena exhausted (internal sizing error)");
             PhraseQuery trial = B.pqs[pi];
-            bool ok = B.phrase_missing[pi] || sa_phrase_guess_ok(trial, st[pi]);
+            bool ok = st[pi].overflow == 0 && (B.phrase_missing[pi] || sa_phrase_guess_ok(trial, st[pi]));
             if (!ok || ovf[C.row0 + C.n_term + i]) redo.push_back({true, pi, B.phrase_query[pi], nullptr});
         }
     }

@@ -843,6 +843,182 @@ __device__ void phrase_work_staged(const PhraseArgs &a, const u32 q, const u32 c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The CONJUNCTION regime (balanced lists): one CTA per (query, 8192-doc tile), like the term scan -- small shared
+// memory footprint, five CTAs per SM, latency hidden by occupancy.  A doc can only match if it holds EVERY term of the
+// phrase, so the CTA streams the tile's slice of every term ONCE with coalesced loads and sets bits in per-term
+// doc-presence bitmaps (shared-memory atomicOr), ANDs them, and in the (rare) tiles where candidate docs exist each
+// warp takes its 1,024 docs: lane-parallel binary searches for its sub-slice bounds, ordered compaction of the
+// candidates' words by ballots, the whole bigram chain at warp scope (sa_phrase_warp.cuh) -- all inside the warp's own
+// 4 KB of the tile.  HBM traffic: 8 * sum(W) + 4 * N, each list read once, sequentially: the B_phrase of SURVEY 8d
+// without its continuation term.  A sub-range whose candidates do not fit its compaction area flags the query for
+// the exact re-run in the search regime (the host routes phrases whose terms co-occur that often there up front).
+__global__ void __launch_bounds__(PT, 5)
+phrase_tile_kernel(const PhraseArgs a) {
+    __shared__ __align__(16) float s_tile[SA_TILE_DOCS];
+    __shared__ u32 s_top[(PT / 32) * 8];
+    __shared__ u32 s_ncand, s_tile_max;
+    __shared__ u32 s_wmatch[PT / 32];
+    __shared__ const u64 *s_ptr[PT / 32][SA_MAX_PHRASE_TERMS];
+    __shared__ u32 s_n[PT / 32][SA_MAX_PHRASE_TERMS];
+
+    const u32 q = a.qsel ? a.qsel[blockIdx.x] : blockIdx.x;
+    const u32 tile = blockIdx.y;
+    const PhraseQuery &pq = a.queries[q];
+    const u32 n_terms = pq.n_terms;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
+    const u64 td1 = min(td0 + SA_TILE_DOCS, a.doc_base + a.n_docs);
+    float *out = a.out + (u64)q * a.out_stride;
+    const u32 row = a.topk_row0 + q;
+
+    // the tile's slice of term `lane`: its tile directory, or (short lists) a search
+    u64 t_lo = 0;
+    u32 t_n = 0;
+    for (u32 t = 0; t < n_terms; t++) {
+        if (pq.dir_plus1[t] && a.tile_dir) continue;
+        const u64 *lst = a.words + pq.off[t];                                  // (all lanes search, lane t keeps the result)
+        const u64 lo = warp_lower_bound_shifted(lst, 0, pq.len[t], td0, SA_KEY_SHIFT);
+        const u64 hi = warp_lower_bound_shifted(lst, lo, pq.len[t], td1, SA_KEY_SHIFT);
+        if (lane == t) { t_lo = lo; t_n = (u32)(hi - lo); }
+    }
+    if (lane < n_terms && pq.dir_plus1[lane] && a.tile_dir) {
+        const u32 *dir = a.tile_dir + (pq.dir_plus1[lane] - 1) + tile;
+        t_lo = __ldg(dir);
+        t_n = __ldg(dir + 1) - (u32)t_lo;
+    }
+    const bool all_present = __all_sync(0xffffffffu, lane >= n_terms || t_n > 0);
+
+    u32 c = 0;                                                                  // candidate docs: 32 per thread
+    if (all_present) {                                                          // CTA-uniform
+        u32 *term_bm = reinterpret_cast<u32 *>(s_tile);                         // [n_terms][256]
+        for (u32 i = tid; i < n_terms * (SA_TILE_DOCS / 32); i += PT) term_bm[i] = 0u;
+        __syncthreads();
+        for (u32 t = 0; t < n_terms; t++) {
+            const u64 *lst = a.words + pq.off[t] + __shfl_sync(0xffffffffu, t_lo, t);
+            const u32 n = __shfl_sync(0xffffffffu, t_n, t);
+            u32 *bm = term_bm + t * (SA_TILE_DOCS / 32);
+            u32 i = tid;
+            for (; i + 3 * PT < n; i += 4 * PT) {                               // four independent loads in flight per thread
+                const u64 w0 = ld_stream_u64(lst + i), w1 = ld_stream_u64(lst + i + PT);
+                const u64 w2 = ld_stream_u64(lst + i + 2 * PT), w3 = ld_stream_u64(lst + i + 3 * PT);
+                const u32 r0 = (u32)((w0 >> SA_KEY_SHIFT) - td0), r1 = (u32)((w1 >> SA_KEY_SHIFT) - td0);
+                const u32 r2 = (u32)((w2 >> SA_KEY_SHIFT) - td0), r3 = (u32)((w3 >> SA_KEY_SHIFT) - td0);
+                atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
+                atomicOr(&bm[r1 >> 5], 1u << (r1 & 31u));
+                atomicOr(&bm[r2 >> 5], 1u << (r2 & 31u));
+                atomicOr(&bm[r3 >> 5], 1u << (r3 & 31u));
+            }
+            for (; i < n; i += PT) {
+                const u32 rel = (u32)((ld_stream_u64(lst + i) >> SA_KEY_SHIFT) - td0);
+                atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
+            }
+        }
+        __syncthreads();
+        c = term_bm[tid];
+        for (u32 t = 1; t < n_terms; t++) c &= term_bm[t * (SA_TILE_DOCS / 32) + tid];
+        __syncthreads();                                                        // the bitmaps are dead: the warps' slices are free
+    }
+
+    // ---- candidate docs (rare): every warp on its own 1,024 docs, inside its own 4 KB of the tile
+    float *my_slice = s_tile + warp * PW_SUB_DOCS;
+    u64 res[2] = {0ull, 0ull};                                                  // this lane's (doc << 32 | count) results
+    u32 n_res = 0;
+    if (__reduce_add_sync(0xffffffffu, (u32)__popc(c))) {                       // warp-uniform
+        u32 *wcand = reinterpret_cast<u32 *>(my_slice);                         // [32]
+        // capacities so that candidates + the chain's six buffers fit in the slice
+        const u32 fb_cap = (PW_SUB_DOCS * 4 - 128 - 96) / (8 * n_terms + 48);
+        u64 *fb = reinterpret_cast<u64 *>(wcand + 32);                          // [n_terms][fb_cap]
+        u64 *chain_buf = fb + (u64)n_terms * fb_cap;                            // 6 x (fb_cap + 2)
+        const u64 w_d0 = td0 + (u64)warp * PW_SUB_DOCS, w_d1 = w_d0 + PW_SUB_DOCS;
+        wcand[lane] = c;
+        // sub-slice bounds: lane 2t searches the lower, lane 2t+1 the upper doc bound of term t (global memory, L2-hot)
+        u32 bound = 0;
+        {
+            const u32 t = lane >> 1;
+            const u64 lo_t = __shfl_sync(0xffffffffu, t_lo, t);
+            const u32 n = __shfl_sync(0xffffffffu, t_n, t);
+            if (t < n_terms) bound = w_lower_bound_doc(a.words + pq.off[t] + lo_t, n, (lane & 1u) ? w_d1 : w_d0);
+        }
+        __syncwarp();
+        bool fits = true;
+        for (u32 t = 0; t < n_terms; t++) {
+            const u64 *base = a.words + pq.off[t] + __shfl_sync(0xffffffffu, t_lo, t);
+            const u32 lo = __shfl_sync(0xffffffffu, bound, 2 * t), hi = __shfl_sync(0xffffffffu, bound, 2 * t + 1);
+            u64 *dst = fb + (u64)t * fb_cap;
+            u32 kept = 0;
+            for (u32 i0 = lo; i0 < hi; i0 += 32) {                             // ordered compaction by ballots
+                const u32 i = i0 + lane;
+                u64 w = 0;
+                bool keep = false;
+                if (i < hi) {
+                    w = base[i];
+                    const u32 rel = (u32)((w >> SA_KEY_SHIFT) - w_d0);
+                    keep = (wcand[rel >> 5] >> (rel & 31u)) & 1u;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const u32 at = kept + __popc(m & ((1u << lane) - 1u));
+                if (keep && at < fb_cap) dst[at] = w;
+                kept += __popc(m);
+            }
+            fits = fits && kept <= fb_cap;
+            if (lane == 0) { s_ptr[warp][t] = dst; s_n[warp][t] = min(kept, fb_cap); }
+        }
+        __syncwarp();
+        if (fits) {
+            const WarpFin wf = warp_phrase_chain(pq, s_ptr[warp], s_n[warp], chain_buf, fb_cap + 2, &a.stats[q]);
+            n_res = wf.n_docs;                                                   // <= fb_cap + 2 <= 64: two per lane
+            if (lane < n_res) res[0] = wf.docs[lane];
+            if (lane + 32 < n_res) res[1] = wf.docs[lane + 32];
+        } else if (lane == 0) {
+            atomicExch(&a.stats[q].overflow, 2u);                               // dense conjunction: re-run in the search regime
+        }
+        __syncwarp();
+    }
+    // ---- this warp's 4 KB of the dense tile: zeros + its matches
+#pragma unroll
+    for (int i = 0; i < PW_SUB_DOCS / 32 / 4; i++)
+        reinterpret_cast<float4 *>(my_slice)[lane + i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    u32 my_max = 0, my_match = 0;
+    Bm25Params p = a.bm25;
+    p.idf = pq.idf;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        if (lane + 32 * j >= n_res) continue;
+        const u32 cnt = (u32)(res[j] & 0xFFFFFFFFull);
+        if (cnt == 0) continue;
+        const u64 d = (res[j] >> 32) - a.doc_base;
+        if (d >= a.n_docs) continue;
+        my_match++;
+        const float v = a.score ? bm25_one((float)cnt, __ldg(a.doc_lens + d), p) : (float)cnt;
+        s_tile[d - (u64)tile * SA_TILE_DOCS] = v;
+        if (v > 0.0f) my_max = max(my_max, __float_as_uint(v));
+    }
+    my_match = __reduce_add_sync(0xffffffffu, my_match);
+    if (lane == 0) {
+        if (my_match) atomicAdd(&a.stats[q].n_match, my_match);
+        s_wmatch[warp] = my_match;
+    }
+    __syncthreads();
+    u32 total = 0, holders = 0;
+#pragma unroll
+    for (int w = 0; w < PT / 32; w++) { total += s_wmatch[w]; holders += min(s_wmatch[w], 32u); }
+    if (total == 0) {
+        float4 *__restrict__ out4 = reinterpret_cast<float4 *>(out + (u64)tile * SA_TILE_DOCS);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < SA_TILE_DOCS / PT / 4; i++) __stcs(out4 + tid + i * PT, z);
+        if (a.topk.k && tid == 0) {
+            const u64 t_idx = (u64)row * a.topk.n_tiles + tile;
+            a.topk.tile_cnt[t_idx] = 0;
+            a.topk.tile_max[t_idx] = 0;
+        }
+        return;
+    }
+    flush_tile_collect(s_tile, out + (u64)tile * SA_TILE_DOCS, a.topk, row, tile, my_max, total, holders, s_top, &s_ncand, &s_tile_max);
+}
+
 // Persistent CTAs (grid = resident CTAs of the device): work items (query, chunk) are claimed with an atomic
 // counter, each CTA keeps its staging buffer (dynamic shared memory, two halves), its mbarriers and its scratch slab.
 __global__ void __launch_bounds__(PT, 2)
@@ -904,12 +1080,18 @@ u32 sa_phrase_stage_words() {
 
 // Merge regime or search regime?  Staging reads every list once (8 * sum(W) bytes); the search path costs about
 // `ratio` bytes (a dozen 32-byte sectors of dependent probes) per driver element of the first step.
-bool sa_phrase_is_staged(const PhraseQuery &pq) {
+bool sa_phrase_is_staged(const PhraseQuery &pq, u64 n_docs) {
     static const long env = getenv("SA_PHRASE_STAGE_RATIO") ? atol(getenv("SA_PHRASE_STAGE_RATIO")) : -1;
     const u64 ratio = env >= 0 ? (u64)env : 50;
     if (ratio == 0) return false;
     const u32 n = pq.n_terms;
     if (n < 2) return false;
+    // expected candidate words per 1,024-doc sub-range (terms taken as independent): they must fit the warp's
+    // compaction area with room to spare, or the conjunction regime would keep bouncing the query to the search regime
+    double est = (double)PW_SUB_DOCS;
+    for (u32 t = 0; t < n; t++) est *= std::min(1.0, (double)pq.len[t] / (double)std::max<u64>(n_docs, 1));
+    const double fb_cap = (double)((PW_SUB_DOCS * 4 - 128 - 96) / (8 * n + 48));
+    if (est * 1.5 * 3.0 > fb_cap) return false;
     u64 sum = 0, drive = ~0ull;
     for (u32 t = 0; t < n; t++) {
         sum += pq.len[t];
@@ -991,7 +1173,7 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         arena_words += 6 * (sum + 2ull * n_chunks);
     }
     // merge regime (single query on the index's own lists): persistent CTAs + TMA staging, no bump arena
-    bool staged = staged_slab_cap && Q == 1 && d_words == ix->d_words && !dump.cont && sa_phrase_is_staged(pqs[0]);
+    bool staged = staged_slab_cap && Q == 1 && d_words == ix->d_words && !dump.cont && sa_phrase_is_staged(pqs[0], ix->n_docs);
     const u64 full_arena_words = arena_words;
     const std::vector<PhraseQuery> pqs_in = pqs;
     if (staged) arena_words = 64;
@@ -1045,7 +1227,8 @@ int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d
         SA_CUDA(cudaStreamSynchronize(ix->stream));
         bool again = false;
         for (u32 q = 0; q < Q; q++) {
-            SA_CHECK(!h_stats[q].overflow, "phrase scratch arena exhausted (internal sizing error)");
+            SA_CHECK(h_stats[q].overflow != 1, "phrase scratch arena exhausted (internal sizing error)");
+            if (h_stats[q].overflow == 2) { again = true; continue; }      // dense conjunction: the search regime takes it
             step_order(pqs[q], order);
             for (u32 s : order) {
                 bool actual = h_stats[q].n_inner[s] > 0 && h_stats[q].n_diff[s] == 0;
@@ -1144,7 +1327,22 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
         a.n_sel = split->n_search;
         if ((rc = launch_phrase(ix, a, split->n_search))) return rc;
     }
-    // merge regime: persistent CTAs, TMA-staged segments
+    a.qsel = split->d_staged;
+    a.n_sel = split->n_staged;
+    static const bool use_tma_pipeline = getenv("SA_PHRASE_TMA_PIPELINE") && atoi(getenv("SA_PHRASE_TMA_PIPELINE")) != 0;
+    if (!use_tma_pipeline) {
+        // conjunction regime: one CTA per (query, tile), like the term scan
+        const unsigned n_tiles = (unsigned)((ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+        KernelTimer t(ix, 2);
+        phrase_tile_kernel<<<dim3(split->n_staged, n_tiles), PT, 0, ix->stream>>>(a);
+        SA_CUDA(cudaGetLastError());
+        t.stop();
+        ix->stats.phrase_kernel_launches++;
+        ix->stats.total_launches++;
+        return SA_OK;
+    }
+    // the same regime as persistent CTAs with a double-buffered TMA pipeline (kept for comparison: measured slower,
+    // profiles/README.md): SA_PHRASE_TMA_PIPELINE=1
     const u32 stage_words = sa_phrase_stage_words();
     u32 ctas = 0;
     if ((rc = staged_grid(ix, stage_words, &ctas))) return rc;

@@ -24,7 +24,7 @@ struct PhraseQuery {
 struct PhraseStats {      // per query, accumulated over all chunks (global atomics)
     u32 n_inner[SA_MAX_PHRASE_TERMS];   // equal-header pairs seen at step s
     u32 n_diff[SA_MAX_PHRASE_TERMS];    // ... of which lhs word != rhs word
-    u32 overflow;                        // scratch arena exhausted
+    u32 overflow;                        // 1: scratch arena exhausted; 2: conjunction regime gave up (dense candidates) -> search regime
     u32 n_match;                         // docs with a non-zero phrase count (M of SURVEY 8d's B_phrase)
     unsigned long long n_cont;           // continuation words written over all steps (sum of C_s)
 };
@@ -90,7 +90,7 @@ int sa_phrase_enqueue(sa_index *ix, const PhraseQuery *d_pqs, PhraseStats *d_sta
 u32 sa_phrase_staged_chunks(const sa_index *ix);
 u64 sa_phrase_slab_cap(const sa_index *ix, const u32 *term_ids, u32 n_terms);
 u32 sa_phrase_chunks(const sa_index *ix, u32 wanted);
-bool sa_phrase_is_staged(const PhraseQuery &pq);
+bool sa_phrase_is_staged(const PhraseQuery &pq, u64 n_docs);
 u32 sa_phrase_stage_words();
 int sa_phrase_run_sync(sa_index *ix, std::vector<PhraseQuery> &pqs, const u64 *d_words,
                        int score, const Bm25Params &p, u32 n_chunks_hint, PhraseDump dump, u64 staged_slab_cap);
