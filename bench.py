@@ -672,6 +672,9 @@ def bench_ours(args, rank, world):
         if args.slop_queries > 0:
             phrase["slop2"] = phrase_block(pq_all[:args.slop_queries], 2,
                                            "4-term phrase, slop 2 (BASELINE configs[3]), same batched top-%d API" % k, False)
+            if rare_q and hard_q and args.slop_queries >= 64:
+                phrase["slop2_rare"] = phrase_block(rare_q[:args.slop_queries], 2, "4-term phrase, slop 2, rare-term stratum", False)
+                phrase["slop2_hard"] = phrase_block(hard_q[:args.slop_queries], 2, "4-term phrase, slop 2, hard stratum", False)
         bq = synth.bigram_queries(spec, args.bigram_queries)
         if bq:
             bigram = phrase_block(bq, 0, "bigram common (df/N 3e-1) x mid (df/N 3e-2), slop 0 (BASELINE.md's 4.5M x 0.45M-word "

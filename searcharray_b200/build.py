@@ -53,8 +53,9 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _newer(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]   # NCCL is dlopen'ed (sa_comm.cu)
+        cmd = [nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-lcudart", "-ldl"]   # NCCL is dlopen'ed (sa_comm.cu)
         subprocess.check_call(cmd)
+        os.replace(LIB + ".tmp", LIB)          # atomic: a concurrent reader never sees a half-written library
     return LIB
 
 

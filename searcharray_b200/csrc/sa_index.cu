@@ -828,7 +828,7 @@ int sa_batch_upload_locked(sa_index *ix, const uint32_t *terms, const uint32_t *
                         dirs[i] = missing ? SA_NO_DIR : ix->h_dir_off[tids[i]];
                         literal = literal && !missing && ix->h_first0[tids[i]];
                     }
-                    sa_span_plan_add(plan, offs, lens, dirs, nt, slop, idf[q], literal);
+                    sa_span_plan_add(plan, offs, lens, dirs, nt, slop, idf[q], literal, missing ? 0 : ix->n_docs);
                     B.span_idf.push_back(idf[q]);
                     B.phrase_query.push_back(q);
                 } else {

@@ -63,6 +63,8 @@ struct SpanArgs {
     u32 topk_row0;
     u32 n_chunks;                        // doc-range chunks per query of span_tiles_kernel
     u64 docs_per_chunk;                  // a multiple of SA_TILE_DOCS
+    u32 *cand_bits;                      // candidate-doc bitmaps (conjunction prefilter), one bit per local doc
+    const u32 *conj;                     // indices of the queries that have one
 };
 
 // first index in [0, len) whose header is >= target
@@ -130,6 +132,49 @@ __device__ __forceinline__ u32 block_scan_excl_max(u32 v, u32 *warp_max, u32 &to
     return max(base, excl);
 }
 
+// ---------------------------------------------------------------------------- phase 0 (balanced lists)
+// A header can only become a candidate if every term has a word within one block of it -- in particular the doc
+// holds EVERY term.  For balanced lists that conjunction is rare, and testing it per generator word by searching
+// every list is what phase 1 spends its time on; so these queries first get a candidate-doc bitmap, built like the
+// phrase conjunction regime does (sa_phrase.cu): one CTA per (query, 8192-doc tile) streams the tile's slice of
+// every term once, sets bits in per-term presence bitmaps (shared-memory atomicOr) and ANDs them.  Phase 1 then
+// skips every generator word whose doc is not a candidate (its five candidates cannot pass the presence test).
+__global__ void __launch_bounds__(256)
+span_cand_kernel(const SpanArgs a) {
+    __shared__ u32 s_bm[SA_MAX_PHRASE_TERMS * (SA_TILE_DOCS / 32)];
+    const SpanQuery &sq = a.queries[a.conj[blockIdx.x]];
+    const u32 tile = blockIdx.y, n = sq.n_terms;
+    const unsigned tid = threadIdx.x;
+    const u64 td0 = a.doc_base + (u64)tile * SA_TILE_DOCS;
+    for (u32 i = tid; i < n * (SA_TILE_DOCS / 32); i += 256) s_bm[i] = 0u;
+    __syncthreads();
+    for (u32 t = 0; t < n; t++) {
+        const u32 *dir = a.tile_dir + sq.dir_off[t] + tile;
+        const u32 lo = __ldg(dir), hi = __ldg(dir + 1);
+        const u64 *__restrict__ lst = a.words + sq.off[t];
+        u32 *bm = s_bm + t * (SA_TILE_DOCS / 32);
+        u32 i = lo + tid;
+        for (; i + 3 * 256 < hi; i += 4 * 256) {
+            const u64 w0 = ld_stream_u64(lst + i), w1 = ld_stream_u64(lst + i + 256);
+            const u64 w2 = ld_stream_u64(lst + i + 512), w3 = ld_stream_u64(lst + i + 768);
+            const u32 r0 = (u32)((w0 >> SA_KEY_SHIFT) - td0), r1 = (u32)((w1 >> SA_KEY_SHIFT) - td0);
+            const u32 r2 = (u32)((w2 >> SA_KEY_SHIFT) - td0), r3 = (u32)((w3 >> SA_KEY_SHIFT) - td0);
+            atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
+            atomicOr(&bm[r1 >> 5], 1u << (r1 & 31u));
+            atomicOr(&bm[r2 >> 5], 1u << (r2 & 31u));
+            atomicOr(&bm[r3 >> 5], 1u << (r3 & 31u));
+        }
+        for (; i < hi; i += 256) {
+            const u32 rel = (u32)((ld_stream_u64(lst + i) >> SA_KEY_SHIFT) - td0);
+            atomicOr(&bm[rel >> 5], 1u << (rel & 31u));
+        }
+    }
+    __syncthreads();
+    u32 c = s_bm[tid];
+    for (u32 t = 1; t < n; t++) c &= s_bm[t * (SA_TILE_DOCS / 32) + tid];
+    a.cand_bits[sq.cand_off + (u64)tile * (SA_TILE_DOCS / 32) + tid] = c;
+}
+
 // ---------------------------------------------------------------------------- phase 1
 __global__ void __launch_bounds__(GEN_THREADS)
 span_presence_kernel(const SpanArgs a) {
@@ -154,7 +199,14 @@ span_presence_kernel(const SpanArgs a) {
 
     // A. presence of every term at hs-3 .. hs+3 (bit o <-> header hs + (o-3) blocks)
     u64 mm[2] = {0, 0};                                                 // 8 bits per term
-    if (active) {
+    bool doc_ok = active;
+    if (active && sq.cand_off != SA_NO_DIR) {                           // conjunction prefilter (phase 0)
+        const u64 d = (hs >> SA_KEY_SHIFT) - a.doc_base;
+        doc_ok = (__ldg(a.cand_bits + sq.cand_off + (d >> 5)) >> (d & 31u)) & 1u;
+        if (!doc_ok)
+            for (u32 t = 0; t < n; t++) rec[t] = 0;                     // nothing of this word is kept
+    }
+    if (doc_ok) {
         const u64 target = hs >= 3 * SA_ONE_BLOCK ? hs - 3 * SA_ONE_BLOCK : 0;
         const u64 top = hs + 3 * SA_ONE_BLOCK;
         for (u32 t = 0; t < n; t++) {
@@ -802,7 +854,7 @@ static u64 padded_stride(u64 n_docs) { return (n_docs + SA_TILE_DOCS - 1) / SA_T
 static u64 align_up(u64 v, u64 a) { return (v + a - 1) / a * a; }
 
 void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u64 *dir_offs, u32 n_terms,
-                      u32 slop, float idf, bool literal) {
+                      u32 slop, float idf, bool literal, u64 n_docs) {
     SpanQuery sq;
     memset(&sq, 0, sizeof(sq));
     sq.n_terms = n_terms;
@@ -836,10 +888,24 @@ void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u6
     plan.max_ctas = std::max(plan.max_ctas, sq.n_ctas);
     plan.max_shortest = std::max(plan.max_shortest, shortest_len);
     plan.any_literal |= literal;
+    // conjunction prefilter: balanced lists (the generator list is not much shorter than the rest), all with a directory
+    sq.cand_off = SA_NO_DIR;
+    if (n_docs && !literal && dir_offs && n_terms >= 2) {
+        static const long env = getenv("SA_SPAN_CONJ_RATIO") ? atol(getenv("SA_SPAN_CONJ_RATIO")) : -1;
+        const u64 ratio = env >= 0 ? (u64)env : 50;
+        u64 sum = 0;
+        bool dirs = true;
+        for (u32 t = 0; t < n_terms; t++) { sum += lens[t]; dirs = dirs && dir_offs[t] != SA_NO_DIR; }
+        if (dirs && ratio && shortest_len * ratio > sum) {
+            sq.cand_off = plan.cand_total;
+            plan.cand_total += (n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS * (SA_TILE_DOCS / 32);
+            plan.conj.push_back((u32)plan.qs.size());
+        }
+    }
     plan.qs.push_back(sq);
 }
 
-struct SpanLayout { u64 words, groups, rec, rec2, cta, matches, total; };
+struct SpanLayout { u64 words, groups, rec, rec2, cta, matches, cand, conj, total; };
 static SpanLayout span_layout(const SpanPlan &plan) {
     SpanLayout L;
     L.words = 0;
@@ -848,7 +914,9 @@ static SpanLayout span_layout(const SpanPlan &plan) {
     L.rec2 = align_up(L.rec + plan.rec_total * sizeof(u64), 256);
     L.cta = align_up(L.rec2 + plan.rec_total * sizeof(u32), 256);
     L.matches = align_up(L.cta + plan.cta_total * sizeof(CtaRec), 256);
-    L.total = align_up(L.matches + plan.match_total * sizeof(u64), 256) + 256;
+    L.cand = align_up(L.matches + plan.match_total * sizeof(u64), 256);
+    L.conj = align_up(L.cand + plan.cand_total * sizeof(u32), 256);
+    L.total = align_up(L.conj + plan.conj.size() * sizeof(u32), 256) + 256;
     return L;
 }
 
@@ -906,7 +974,18 @@ int sa_span_enqueue(sa_index *ix, const u64 *d_lists, const SpanPlan &plan, cons
     } else {
         SA_CUDA(cudaMemsetAsync(dense_rows, 0, (size_t)Q * stride * sizeof(float), ix->stream));
     }
+    a.cand_bits = (u32 *)(base + L.cand);
+    a.conj = (const u32 *)(base + L.conj);
     KernelTimer t(ix, 2);
+    if (!plan.conj.empty()) {
+        SA_CHECK(a.tile_dir, "span conjunction prefilter needs the index's own lists");
+        SA_CUDA(cudaMemcpyAsync(base + L.conj, plan.conj.data(), plan.conj.size() * sizeof(u32), cudaMemcpyHostToDevice, ix->stream));
+        const unsigned n_tiles = (unsigned)((ix->n_docs + SA_TILE_DOCS - 1) / SA_TILE_DOCS);
+        span_cand_kernel<<<dim3((unsigned)plan.conj.size(), n_tiles), 256, 0, ix->stream>>>(a);
+        SA_CUDA(cudaGetLastError());
+        ix->stats.phrase_kernel_launches += 1;
+        ix->stats.total_launches += 1;
+    }
     if (plan.max_ctas) {
         dim3 grid(plan.max_ctas, Q);
         span_presence_kernel<<<grid, GEN_THREADS, 0, ix->stream>>>(a);
@@ -966,7 +1045,7 @@ int sa_span_run(sa_index *ix, const u64 *d_lists, const u64 *offs, const u64 *le
     int rc;
     if ((rc = ix->dense.reserve(stride * sizeof(float)))) return rc;
     SpanPlan plan;
-    sa_span_plan_add(plan, offs, lens, dir_offs, n_terms, slop, 0.0f, literal);
+    sa_span_plan_add(plan, offs, lens, dir_offs, n_terms, slop, 0.0f, literal, d_lists == ix->d_words ? ix->n_docs : 0);
     if ((rc = ix->phrase_scratch.reserve(sa_span_scratch_bytes(plan)))) return rc;
     if ((rc = ix->queries.reserve(sizeof(SpanQuery)))) return rc;
     if ((rc = ix->cand_meta.reserve(sizeof(SpanCounts)))) return rc;

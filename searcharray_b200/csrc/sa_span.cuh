@@ -19,6 +19,7 @@ struct SpanQuery {
     u64 g_off[SA_MAX_PHRASE_TERMS];     // group-start region of term t in the u32 arena
     u64 s_cap[SA_MAX_PHRASE_TERMS];
     u64 m_off;                          // match records (one per phase-2 iteration) of this query
+    u64 cand_off;                       // candidate-doc bitmap of this query in the u32 bitmap arena, or SA_NO_DIR
 };
 
 struct SpanCounts {                      // written by phase 1, read by phase 2
@@ -36,11 +37,15 @@ struct SpanPlan {
     u32 max_ctas = 0;
     u64 max_shortest = 0;
     bool any_literal = false;
+    // conjunction prefilter (balanced lists): queries whose candidate-doc bitmap is built before phase 1
+    std::vector<u32> conj;
+    u64 cand_total = 0;                 // u32 words of bitmap arena
 };
 
 // Appends one query.  dir_offs may be NULL (no tile directories, e.g. filtered lists).
+// n_docs != 0 and every list has a directory: balanced queries get the conjunction prefilter.
 void sa_span_plan_add(SpanPlan &plan, const u64 *offs, const u64 *lens, const u64 *dir_offs, u32 n_terms,
-                      u32 slop, float idf, bool literal);
+                      u32 slop, float idf, bool literal, u64 n_docs = 0);
 size_t sa_span_scratch_bytes(const SpanPlan &plan);
 // Enqueues the whole plan.  d_qs: device copy of plan.qs; d_counts: SpanCounts[Q] (zeroed here).
 // topk != NULL (batched path): nothing is pre-zeroed; the matches become per-query records and one
