@@ -234,6 +234,52 @@ edismax_sort_kernel(const u64 *__restrict__ pairs, const unsigned long long *__r
     }
 }
 
+// ---- exact fallback of the top-k when more than ED_TOPK_CAP docs share the leading 32 bits of the k-th score
+// (BM25 scores are a function of (tf, doc length): on a field of uniform short docs thousands of docs tie exactly).
+// hist[b] = docs with score > 0 whose bits match `prefix` above `shift + 8` and whose next byte is b
+__global__ void __launch_bounds__(256)
+edismax_hist_kernel(const double *__restrict__ qf, u64 n_docs, u64 prefix, int shift, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u64 d = (u64)blockIdx.x * blockDim.x + threadIdx.x; d < n_docs; d += (u64)gridDim.x * blockDim.x) {
+        const double v = qf[d];
+        if (!(v > 0.0)) continue;
+        const u64 bits = (u64)__double_as_longlong(v);
+        if (shift < 56 && (bits >> (shift + 8)) != (prefix >> (shift + 8))) continue;
+        atomicAdd(&s_h[(bits >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_h[threadIdx.x]);
+}
+
+// docs scoring strictly more than `kth_bits` (fewer than k of them) -> pairs; ties per 1024-doc block -> tie_cnt
+__global__ void __launch_bounds__(256)
+edismax_above_kernel(const double *__restrict__ qf, u64 n_docs, u64 kth_bits, u64 *__restrict__ pairs,
+                     unsigned long long *__restrict__ count, u32 cap, u32 *__restrict__ tie_cnt) {
+    __shared__ unsigned int s_t;
+    if (threadIdx.x == 0) s_t = 0;
+    __syncthreads();
+    const u64 d0 = (u64)blockIdx.x * 1024;
+    u32 mine = 0;
+    for (u32 i = threadIdx.x; i < 1024; i += 256) {
+        const u64 d = d0 + i;
+        if (d >= n_docs) break;
+        const double v = qf[d];
+        if (!(v > 0.0)) continue;
+        const u64 bits = (u64)__double_as_longlong(v);
+        if (bits > kth_bits) {
+            const unsigned long long slot = atomicAdd(count, 1ull);
+            if (slot < cap) { pairs[2 * slot] = bits; pairs[2 * slot + 1] = d; }
+        } else if (bits == kth_bits) {
+            mine++;
+        }
+    }
+    if (mine) atomicAdd(&s_t, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tie_cnt[blockIdx.x] = s_t;
+}
+
 // ------------------------------------------------------------------------------ host
 extern "C" int sa_multi_create(sa_index *const *fields, uint32_t n_fields, sa_multi **out) {
     SA_CHECK(fields && out && n_fields >= 1 && n_fields <= ED_MAX_FIELDS, "1..%d fields", ED_MAX_FIELDS);
@@ -542,6 +588,67 @@ extern "C" int sa_multi_topk(sa_multi *m, uint32_t k, uint32_t *out_docs, double
     SA_CUDA(cudaMemcpyAsync(out_scores, d_scores, k * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     SA_CUDA(cudaMemcpyAsync(out_docs, d_docs, k * sizeof(u32), cudaMemcpyDeviceToHost, m->stream));
     SA_CUDA(cudaStreamSynchronize(m->stream));
-    SA_CHECK(cnt <= ED_TOPK_CAP, "more than %d docs tie with the k-th score in their leading 32 bits", ED_TOPK_CAP);
+    if (cnt <= ED_TOPK_CAP) return SA_OK;
+
+    // ---- more than ED_TOPK_CAP docs share the k-th score's leading bits: exact selection on the full 64 bits
+    // 1. the k-th largest score (with multiplicity): 8-pass byte-wise radix select over all docs
+    unsigned long long *d_hist = (unsigned long long *)m->d_pairs;             // 256 counters (the pairs buffer is free)
+    unsigned long long h_hist[256];
+    u64 prefix = 0, need = k;
+    const unsigned hb = (unsigned)std::min<u64>(1024, (m->n_docs + 255) / 256);
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        SA_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(h_hist), m->stream));
+        edismax_hist_kernel<<<hb, 256, 0, m->stream>>>(m->d_qf, m->n_docs, prefix, shift, d_hist);
+        SA_CUDA(cudaGetLastError());
+        SA_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, m->stream));
+        SA_CUDA(cudaStreamSynchronize(m->stream));
+        int b = 255;
+        for (; b > 0; b--) {
+            if (h_hist[b] >= need) break;
+            need -= h_hist[b];
+        }
+        prefix |= (u64)b << shift;
+    }
+    const u64 kth_bits = prefix;                     // `need` docs with exactly this score belong to the top k
+    // 2. docs above it (fewer than k) + ties per 1024-doc block
+    const u32 n_blocks = (u32)((m->n_docs + 1023) / 1024);
+    if ((rc = m->cand.reserve((size_t)n_blocks * sizeof(u32) + 64))) return rc;
+    std::vector<u32> tie_cnt(n_blocks);
+    std::vector<u64> above(2 * (size_t)k);
+    SA_CUDA(cudaMemsetAsync(m->d_count, 0, sizeof(unsigned long long), m->stream));
+    edismax_above_kernel<<<n_blocks, 256, 0, m->stream>>>(m->d_qf, m->n_docs, kth_bits, m->d_pairs, m->d_count, k, m->cand.as<u32>());
+    SA_CUDA(cudaGetLastError());
+    SA_CUDA(cudaMemcpyAsync(&cnt, m->d_count, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+    SA_CUDA(cudaMemcpyAsync(tie_cnt.data(), m->cand.p, (size_t)n_blocks * sizeof(u32), cudaMemcpyDeviceToHost, m->stream));
+    SA_CUDA(cudaStreamSynchronize(m->stream));
+    SA_CHECK(cnt < k, "top-k fallback: inconsistent selection");
+    if (cnt) SA_CUDA(cudaMemcpy(above.data(), m->d_pairs, 2 * (size_t)cnt * sizeof(u64), cudaMemcpyDeviceToHost));
+    std::vector<std::pair<u64, u64>> best;           // (score bits, doc)
+    for (u64 i = 0; i < cnt; i++) best.push_back({above[2 * i], above[2 * i + 1]});
+    std::sort(best.begin(), best.end(), [](const std::pair<u64, u64> &x, const std::pair<u64, u64> &y) {
+        return x.first > y.first || (x.first == y.first && x.second < y.second);
+    });
+    // 3. the `need` tied docs with the smallest ids: walk the blocks in order, read only the blocks that hold them
+    u64 want_ties = std::min<u64>(need, (u64)k - cnt);
+    std::vector<double> blk(1024);
+    for (u32 bI = 0; bI < n_blocks && want_ties; bI++) {
+        if (!tie_cnt[bI]) continue;
+        const u64 d0 = (u64)bI * 1024, nb = std::min<u64>(1024, m->n_docs - d0);
+        SA_CUDA(cudaMemcpy(blk.data(), m->d_qf + d0, nb * sizeof(double), cudaMemcpyDeviceToHost));
+        for (u64 i = 0; i < nb && want_ties; i++) {
+            u64 bits;
+            memcpy(&bits, &blk[i], 8);
+            if (blk[i] > 0.0 && bits == kth_bits) { best.push_back({bits, d0 + i}); want_ties--; }
+        }
+    }
+    for (u32 i = 0; i < k; i++) {
+        if (i < best.size()) {
+            memcpy(&out_scores[i], &best[i].first, 8);
+            out_docs[i] = (u32)(best[i].second + m->doc_base);
+        } else {
+            out_scores[i] = 0.0;
+            out_docs[i] = SA_NO_DOC;
+        }
+    }
     return SA_OK;
 }

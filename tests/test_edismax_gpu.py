@@ -78,3 +78,19 @@ def test_edismax_composed_path_matches_device_path(frame_and_golden):
         assert got.dtype == want.dtype
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
         assert np.array_equal(got > 0, want > 0)
+
+
+def test_topk_with_thousands_of_exact_ties():
+    """more than 2,048 docs share the top score exactly (uniform short docs): edismax_topk must still
+    return the k best by (score desc, row asc) instead of raising."""
+    from searcharray_b200 import SearchArray
+    from searcharray_b200.solr import edismax, edismax_topk
+    docs = ["foo"] * 3000 + ["foo bar"] * 2500 + ["bar baz"] * 100 + ["foo"] * 2600
+    frame = pd.DataFrame({"t": SearchArray.index(docs)})
+    for q, k in (("foo", 10), ("foo", 32), ("bar", 7)):
+        want, _ = edismax(frame, q, qf=["t"])
+        order = np.lexsort((np.arange(len(want)), -want))[:k]
+        order = order[want[order] > 0]
+        d, s = edismax_topk(frame, q, qf=["t"], k=k)
+        assert np.array_equal(d[:len(order)], order.astype(np.uint32)), (q, k, d, order)
+        assert np.array_equal(s[:len(order)], want[order])

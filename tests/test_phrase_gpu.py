@@ -176,3 +176,35 @@ def test_batch_topk_mixed_terms_and_phrases():
             assert np.array_equal(got_docs[qi][:len(order)], order.astype(np.uint32)), (q, k)
             np.testing.assert_allclose(got_scores[qi][:len(order)], s[order], rtol=1e-5, atol=0)
             assert np.all(got_docs[qi][len(order):] == 0xFFFFFFFF)
+
+
+SWEEP_PHRASES = ["foo bar baz", "foo bar", "foo foo foo", "foo foo bar", "foo bar bar", "foo bar bar baz buz foo bar",
+                 "foo bar bar baz buz foo foo", "foo foo", "foo foo bar", "foo bar bar"]
+
+
+def _sweep_shapes(prefix_and_phrase):
+    """the three corpus shapes of reference test/test_phrase_matches.py:249-299 and what each must return"""
+    return [([prefix_and_phrase, "not match"], [1, 0]),
+            (["not match"] * 100 + [prefix_and_phrase], [0] * 100 + [1]),
+            ((["not match"] + [prefix_and_phrase]) * 100, ([0] + [1]) * 100)]
+
+
+@pytest.mark.parametrize("phrase", SWEEP_PHRASES)
+def test_block_boundary_sweep_at_reference_size(phrase):
+    """reference test/test_phrase_matches.py:249-299 at its own size: 10 phrases x 100 position offsets x 3 corpus
+    shapes, one small index per case, with the reference's two follow-up assertions: every bigram of the phrase
+    matches wherever the phrase does (:205-212), and slop 1..3 match wherever slop 0 does (:215-222)."""
+    from searcharray_b200 import SearchArray
+    toks = phrase.split()
+    for off in range(100):
+        text = " ".join(["dummy"] * off) + " " + phrase
+        for docs, expected in _sweep_shapes(text):
+            arr = SearchArray.index(docs)
+            got = arr.termfreqs(toks)
+            assert np.array_equal(got, np.asarray(expected, dtype=np.float32)), (phrase, off, len(docs))
+            if off % 9 == 0 or len(docs) == 2:
+                hit = got > 0
+                for a, b in zip(toks[:-1], toks[1:]):
+                    assert np.all(arr.termfreqs([a, b])[hit] > 0), (phrase, off, a, b)
+                for slop in (1, 2, 3):
+                    assert np.all(arr.termfreqs(toks, slop=slop)[hit] > 0), (phrase, off, slop)
