@@ -111,16 +111,25 @@ __global__ void df_kernel(const u64 *__restrict__ words, u64 n_words,
                           const u64 *__restrict__ term_off_sorted, const u32 *__restrict__ term_of_slot,
                           u32 n_slots, u32 *__restrict__ df) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
+    const bool live = i < n_words;
     // slot = last j with term_off_sorted[j] <= i   (slots cover [off, off+len) disjointly)
     u32 lo = 0, hi = n_slots;
-    while (hi - lo > 1) {
-        u32 mid = (lo + hi) >> 1;
-        if (term_off_sorted[mid] <= i) lo = mid; else hi = mid;
+    bool head = false;
+    if (live) {
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (term_off_sorted[mid] <= i) lo = mid; else hi = mid;
+        }
+        const u64 start = term_off_sorted[lo];
+        head = (i == start) || ((words[i] >> SA_KEY_SHIFT) != (words[i - 1] >> SA_KEY_SHIFT));
     }
-    u64 start = term_off_sorted[lo];
-    bool head = (i == start) || ((words[i] >> SA_KEY_SHIFT) != (words[i - 1] >> SA_KEY_SHIFT));
-    if (head) atomicAdd(&df[term_of_slot[lo]], 1u);
+    // a warp's 32 consecutive words almost always belong to one term: one atomic per (warp, term) instead of one
+    // per doc head (a billion same-address atomics on a 10M-doc index)
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (heads == 0) return;
+    const unsigned peers = __match_any_sync(0xffffffffu, live ? lo : 0xFFFFFFFFu);
+    const unsigned mine = heads & peers;
+    if (live && mine && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&df[term_of_slot[lo]], (u32)__popc(mine));
 }
 
 // Tile directory of a long posting list: dir[j] = index (within the list) of the first word whose
