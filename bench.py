@@ -47,6 +47,12 @@ def log(*a):
         print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+def dbg(*a):
+    """progress marks of EVERY rank (SA_BENCH_DEBUG=1): where a multi-rank run is, should it ever stall"""
+    if os.environ.get("SA_BENCH_DEBUG"):
+        print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() % 1000:.1f}s]", *a, file=sys.stderr, flush=True)
+
+
 # --------------------------------------------------------------------------- corpus
 def build_corpus(n_docs, rank, world, field="body"):
     from searcharray_b200 import synth
@@ -314,8 +320,10 @@ class Ours:
         self.h = self.dev.handle
         self.ms = ctypes.c_double(0)
         self.n_over = ctypes.c_uint32(0)
+        dbg("uploaded")
         if world > 1:
             self._init_comm()
+        dbg("comm ready")
         L, h = self.L, self.h
         df = np.zeros(self.host.n_terms, dtype=np.uint64)
         tmp = ctypes.c_uint64(0)
@@ -326,6 +334,7 @@ class Ours:
         if world > 1:
             _lib.check(L.sa_comm_allreduce_sum_u64(h, _lib.p_u64(df), len(df)))
         self.df = df                       # GLOBAL document frequencies (idf must not depend on sharding)
+        dbg("global df done")
 
     def _init_comm(self):
         _lib, L, h, rank, world = self._lib, self.L, self.h, self.rank, self.world
@@ -333,6 +342,10 @@ class Ours:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG", None)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sa_b200_nccl_%h_%p.log")
+        # one node, NVLink/NVSwitch between the GPUs: the bootstrap sockets stay on loopback and NCCL does not probe
+        # InfiniBand / network plugins (probing them made ncclCommInitRank take 18 s here, and once never return)
+        os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
         # Rendezvous for the NCCL unique id without any framework: all ranks of one launch share a
         # node (contract: --nnodes=1) and a parent (the torchrun agent), so rank 0 publishes the id
         # in a file keyed by MASTER_PORT + parent pid and the others poll for it.
@@ -475,6 +488,7 @@ def bench_ours(args, rank, world):
     overflow = 0
     for _ in range(max(args.warmup, 3)):
         overflow += e2e_step()
+        dbg("warm-up step done")
 
     # ---- value: device-resident, K x execute between CUDA events on the library stream
     o.upload(term_ids, starts, idf, 0, k)
@@ -484,6 +498,7 @@ def bench_ours(args, rank, world):
     launches_value = int(o.stats().total_launches)
     o.download(out_docs, out_scores)
     value = args.steps * Q / (dev_ms / 1e3)
+    dbg("device-timed steps done")
 
     # ---- e2e: host buffers in, top-k out, every step
     o.barrier()
@@ -558,6 +573,7 @@ def bench_ours(args, rank, world):
                         "achieved": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9,
                         "frac": float(alg_q[sel].sum()) / (ms_b / 1e3) / 1e9 / peak})
     roofline["by_df_bucket"] = buckets
+    dbg("buckets done")
     o.upload(term_ids, starts, idf, 0, k)
 
     # ---- verify: GPU top-k (docs AND score bits) against the oracle, rank 0 holds the FULL corpus
@@ -581,6 +597,7 @@ def bench_ours(args, rank, world):
                                "what": "global top-%d doc ids and score bits vs the CPU oracle" % k}}
             log("verify term:", verify["term"])
 
+    dbg("term verify done")
     # ---- phrase workloads (BASELINE configs[2] and [3]) as extra blocks
     phrase = None
     bigram = None
@@ -600,14 +617,17 @@ def bench_ours(args, rank, world):
         end to end (upload + execute + top-k download), B_phrase roofline, parity sample."""
         ids, p_terms, p_starts, p_idf = phrase_batch(queries, slop)
         PQ = len(queries)
+        dbg("phrase block start:", label[:48], "slop", slop, "queries", PQ)
         p_docs = np.empty((PQ, k), dtype=np.uint32)
         p_scores = np.empty((PQ, k), dtype=np.float32)
         p_redo = 0
         for _ in range(3):
             o.upload(p_terms, p_starts, p_idf, slop, k); o.execute(); p_redo += o.download(p_docs, p_scores)
+        dbg("  warm-up done, repairs", p_redo)
         o.upload(p_terms, p_starts, p_idf, slop, k)
         p_steps = max(2, args.steps)
         p_ms = o.timed_executes(p_steps)
+        dbg("  timed done")
         _lib.check(L.sa_stats_reset(h))
         o.execute()
         o.download(p_docs, p_scores)
@@ -703,6 +723,7 @@ def bench_ours(args, rank, world):
                                      "mean_matching_docs": matched / len(ids)}
         o.upload(term_ids, starts, idf, 0, k)          # restore the term batch for the sections below
 
+    dbg("phrase blocks done")
     # ---- edismax (the shape of BASELINE configs[4], on this run's corpus size): two fields, mixed
     #      2-5 term queries, qf + pf + pf2 + pf3, mm=2, tie=0.3 (reference test_msmarco.py:436-443)
     edis = None

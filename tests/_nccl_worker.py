@@ -21,6 +21,8 @@ K1, B = 1.2, 0.75
 
 def main():
     rank, world, key = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")          # one node: bootstrap over loopback, no IB probing
+    os.environ.setdefault("NCCL_IB_DISABLE", "1")
     n_docs, k = 400_000, 10
     L = _lib.lib()
     spec = synth.SynthSpec(n_docs, terms_per_bucket=3, n_phrases=12, n_bigrams=2)
