@@ -219,4 +219,5 @@ int launch_topk_merge(sa_index *ix, const u64 *d_in, u64 rank_stride, u32 world,
     return SA_OK;
 }
 
-u32 sa_topk_slots(u32 k) { return k <= 16 ? 64u : 128u; }
+// a tile keeps up to 4 * k docs at or above its bound (four docs per thread on the dense tf-table path) plus ties
+u32 sa_topk_slots(u32 k) { return k <= 16 ? 128u : 256u; }
