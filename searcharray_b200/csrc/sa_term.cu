@@ -71,6 +71,7 @@ term_tile_kernel(const TermBatchArgs a) {
     for (int i = 0; i < SA_TILE_DOCS / SA_TERM_THREADS / 4; i++)
         reinterpret_cast<float4 *>(s_out)[tid + i * SA_TERM_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
     u32 lo, hi;
+    bool quads = false;
     // tf-table path (CTA-uniform): the term has (doc, tf) records and nothing has to look inside the words
     const bool use_recs = !FILTER && !ALL_DOCS && a.recs != nullptr && tq.rec_off != SA_NO_DIR && tq.dir_off != SA_NO_DIR;
     if (use_recs) {
@@ -78,6 +79,11 @@ term_tile_kernel(const TermBatchArgs a) {
         lo = __ldg(dir);
         hi = __ldg(dir + 1);
         __syncthreads();
+        // Four records per thread only when that still leaves >= k threads, in whole warps, holding a score: the
+        // tile bound is the k-th largest of (at most 8 per warp) thread maxima, and with fewer than k of them it
+        // degenerates to "keep everything" -- 129 records in 32 threads of ONE warp overflowed the 128 slots (the short
+        // last tile of a 2.5M-doc shard).  16 * k records = 4 * k quads = k / 8 full warps of 8 published maxima.
+        quads = hi - lo >= max(160u, 16u * a.topk.k);
     } else if (tq.dir_off != SA_NO_DIR) {                             // CTA-uniform
         const u32 *dir = a.tile_dir + tq.dir_off + tile;
         lo = __ldg(dir);
@@ -198,7 +204,7 @@ term_tile_kernel(const TermBatchArgs a) {
         //     lane takes FOUR records with one 16-byte load (record runs start 16-byte aligned; the slice is
         //     widened to whole quads and the strangers masked); no run detection, no shuffles, no popcount.
         const u32 *__restrict__ recs = a.recs + tq.rec_off;
-        if (hi - lo >= 128u) {             // >= 32 quads; with a tile bound over thread maxima at most 4 * k docs reach it
+        if (quads) {                       // with a tile bound over thread maxima at most 4 * k docs reach it
             for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
                 const u32 i = base + tid * 4;
                 uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
@@ -278,7 +284,7 @@ term_tile_kernel(const TermBatchArgs a) {
     const u32 k = a.topk.k;
     const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
     // threads that can hold a score: one per record / posting word, or one per quad of records on the dense tf-table path
-    const u32 M = tile_bound_width(k, (use_recs && hi - lo >= 128u) ? (hi - lo) / 4u : (hi - lo));
+    const u32 M = tile_bound_width(k, quads ? (hi - lo) / 4u : (hi - lo));
     if (need_bound) {
         u32 v = my_max;
         for (u32 r = 0; r < M; r++) {

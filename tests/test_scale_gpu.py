@@ -128,3 +128,34 @@ def test_10m_docs_baseline_size():
     """BASELINE configs[1]-[3] at their stated size (10M docs), reduced vocabulary to bound the test time."""
     spec, host, arr, oidx = build(10_000_000, terms_per_bucket=2, n_phrases=8, n_bigrams=2)
     check_corpus(spec, host, arr, oidx, terms_per_bucket=1, n_rare=3, n_hard=2, n_bigram=1, n_slop=2)
+
+
+def test_short_last_tile_needs_no_exact_rerun():
+    """A shard whose LAST tile is short: a df-0.1 term leaves ~130-160 (doc, tf) records there.  Read four per thread
+    they sat in the threads of one warp, fewer than k thread maxima existed, the tile bound fell to "keep everything"
+    and 129+ candidates overflowed the 128 slots -- every such query paid the exact re-run (4 per step of the 4-GPU
+    bench, 4-9 of the 8-GPU one).  Now: zero re-runs, and the top-k is still the oracle's."""
+    import ctypes
+    from searcharray_b200 import _lib
+    spec, host, arr, oidx = build(8192 * 40 + 1440, n_terms=256, n_phrases=8, n_hard=2, n_bigrams=2)
+    names = list(spec.bucket_terms[1]) + list(spec.bucket_terms[0][:8]) + list(spec.bucket_terms[2][:8])
+    k = 10
+    docs, scores = arr.search_topk(names, k=k)
+    for i, nm in enumerate(names):
+        wd, ws = oracle_topk(oidx.score(spec.term_index[nm], k1=K1, b=B), k)
+        assert np.array_equal(docs[i], wd) and bits_equal(scores[i], ws), nm
+    # the same queries through the batch API, which reports how many took the exact path
+    dev = arr._device()
+    L, h = _lib.lib(), dev.handle
+    tids = np.asarray([spec.term_index[nm] for nm in names], dtype=np.uint32)
+    starts = np.arange(len(tids) + 1, dtype=np.uint32)
+    idf = np.full(len(tids), 2.0, dtype=np.float32)
+    out_d = np.empty((len(tids), k), dtype=np.uint32)
+    out_s = np.empty((len(tids), k), dtype=np.float32)
+    n_over = ctypes.c_uint32(7)
+    _lib.check(L.sa_batch_upload(h, _lib.p_u32(tids), _lib.p_u32(starts), _lib.p_f32(idf), len(tids), 0,
+                                 float(host.avg_doc_length), K1, B, k))
+    _lib.check(L.sa_batch_execute(h))
+    _lib.check(L.sa_batch_download(h, _lib.p_u32(out_d), _lib.p_f32(out_s), ctypes.byref(n_over)))
+    assert n_over.value == 0
+    assert np.array_equal(out_d, docs)
