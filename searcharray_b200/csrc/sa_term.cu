@@ -78,12 +78,22 @@ term_tile_kernel(const TermBatchArgs a) {
         const u32 *dir = a.rec_dir + tq.dir_off + tile;
         lo = __ldg(dir);
         hi = __ldg(dir + 1);
+        // L2 prefetch of the records a LATER tile of this query will read: the grid is (queries, tiles) with the query
+        // fastest, so tile + prefetch_tiles is dispatched about one generation of resident CTAs after this one; its
+        // record loads -- the second of two dependent DRAM round trips (directory, then records) on a memory system
+        // saturated with the dense rows' stores -- then hit L2.  One 128-byte line per thread covers any tile (<= 32 KB).
+        const u32 pf_tile = tile + a.prefetch_tiles;
+        if (a.prefetch_tiles && (u64)pf_tile * SA_TILE_DOCS < a.n_docs) {
+            const u32 plo = __ldg(dir + a.prefetch_tiles), phi = __ldg(dir + a.prefetch_tiles + 1);
+            const u32 pi = (plo & ~31u) + tid * 32u;
+            if (pi < phi) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.recs + tq.rec_off + pi));
+        }
         __syncthreads();
         // Four records per thread only when that still leaves >= k threads, in whole warps, holding a score: the
         // tile bound is the k-th largest of (at most 8 per warp) thread maxima, and with fewer than k of them it
         // degenerates to "keep everything" -- 129 records in 32 threads of ONE warp overflowed the 128 slots (the short
         // last tile of a 2.5M-doc shard).  16 * k records = 4 * k quads = k / 8 full warps of 8 published maxima.
-        quads = hi - lo >= max(160u, 16u * a.topk.k);
+        quads = hi - lo >= max(a.quad_min_recs, 16u * a.topk.k);
     } else if (tq.dir_off != SA_NO_DIR) {                             // CTA-uniform
         const u32 *dir = a.tile_dir + tq.dir_off + tile;
         lo = __ldg(dir);
@@ -107,7 +117,7 @@ term_tile_kernel(const TermBatchArgs a) {
     // norms are > 0 here and scores >= +0, so the sign bit tells a score (set) from a leftover norm
     // (clear), which the flush turns into 0.
     const bool staged_norm = MODE == TERM_MODE_SCORE && !ALL_DOCS &&
-                             (hi - lo) >= (use_recs ? (u32)SA_STAGED_NORM_MIN_RECS : a.staged_norm_min_words);
+                             (hi - lo) >= (use_recs ? a.staged_norm_min_recs : a.staged_norm_min_words);
     bool norm_ready = !staged_norm;
     if (staged_norm) {
         const float4 *__restrict__ n4 = reinterpret_cast<const float4 *>(a.norm + tile_doc0);
@@ -205,16 +215,16 @@ term_tile_kernel(const TermBatchArgs a) {
         //     widened to whole quads and the strangers masked); no run detection, no shuffles, no popcount.
         const u32 *__restrict__ recs = a.recs + tq.rec_off;
         if (quads) {                       // with a tile bound over thread maxima at most 4 * k docs reach it
-            for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4) {       // CTA-uniform trip count
-                const u32 i = base + tid * 4;
-                uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
-                if (i < hi) r4 = __ldg(reinterpret_cast<const uint4 *>(recs + i));
-                const u32 rr[4] = {r4.x, r4.y, r4.z, r4.w};
-                float nr4[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-                if (MODE == TERM_MODE_SCORE && !staged_norm) {
+            // quads => staged norms (quad_min_recs >= staged_norm_min_recs, launch_term_batch): no norm gathers here.
+            // Two quads are loaded before either is processed (two 16-byte loads in flight per thread).
+            constexpr int QU = 2;
+            for (u32 base = lo & ~3u; base < hi; base += SA_TERM_THREADS * 4 * QU) {  // CTA-uniform trip count
+                uint4 r4[QU];
     #pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (i + e >= lo && i + e < hi) nr4[e] = __ldg(norm + (rr[e] >> SA_REC_TF_BITS));
+                for (int u = 0; u < QU; u++) {
+                    const u32 i = base + (u * SA_TERM_THREADS + tid) * 4;
+                    r4[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < hi) r4[u] = __ldg(reinterpret_cast<const uint4 *>(recs + i));
                 }
                 if (!norm_ready) {                             // CTA-uniform: first pass of a staged tile
                     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -222,18 +232,23 @@ term_tile_kernel(const TermBatchArgs a) {
                     norm_ready = true;
                 }
     #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (i + e < lo || i + e >= hi) continue;
-                    const u32 rel = rr[e] >> SA_REC_TF_BITS, tf = rr[e] & SA_REC_TF_MASK;
-                    float v = (float)tf;
-                    if (MODE == TERM_MODE_SCORE) {
-                        v = 0.0f;
-                        if (tf) {
-                            v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : nr4[e], tq.idf);
-                            my_max = max(my_max, __float_as_uint(v));
+                for (int u = 0; u < QU; u++) {
+                    const u32 i = base + (u * SA_TERM_THREADS + tid) * 4;
+                    const u32 rr[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+    #pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (i + e < lo || i + e >= hi) continue;
+                        const u32 rel = rr[e] >> SA_REC_TF_BITS, tf = rr[e] & SA_REC_TF_MASK;
+                        float v = (float)tf;
+                        if (MODE == TERM_MODE_SCORE) {
+                            v = 0.0f;
+                            if (tf) {
+                                v = bm25_from_norm((float)tf, staged_norm ? s_out[rel] : 1.0f, tq.idf);
+                                my_max = max(my_max, __float_as_uint(v));
+                            }
                         }
+                        s_out[rel] = staged_norm ? -v : v;
                     }
-                    s_out[rel] = staged_norm ? -v : v;
                 }
             }
         } else {
@@ -282,7 +297,9 @@ term_tile_kernel(const TermBatchArgs a) {
     //    score fits.  Otherwise each warp publishes its largest thread maxima and every warp
     //    derives the same tile bound; scores >= bound are this tile's candidates.
     const u32 k = a.topk.k;
-    const bool need_bound = k && (hi - lo) > k;                      // CTA-uniform (<= k words: all fit)
+    // CTA-uniform (<= k postings: all fit).  Keeping every positive score of tiles with up to `slots` postings instead
+    // was measured slower (df/N 1e-2: 9.9 vs 9.2 us/query): candidates cost more than the bound.
+    const bool need_bound = k && (hi - lo) > k;
     // threads that can hold a score: one per record / posting word, or one per quad of records on the dense tf-table path
     const u32 M = tile_bound_width(k, quads ? (hi - lo) / 4u : (hi - lo));
     if (need_bound) {
@@ -482,8 +499,13 @@ int launch_term_batch(sa_index *ix, const TermBatchArgs &a_in, u32 n_queries) {
     if (n_queries == 0 || a_in.n_docs == 0) return SA_OK;
     TermBatchArgs a = a_in;
     {
-        static const long env_thresh = getenv("SA_STAGED_NORM_MIN_WORDS") ? atol(getenv("SA_STAGED_NORM_MIN_WORDS")) : -1;
-        a.staged_norm_min_words = env_thresh >= 0 ? (u32)env_thresh : SA_STAGED_NORM_MIN_WORDS;
+        // tuning knobs, read per launch (a getenv costs nanoseconds; tools/term_buckets.py sweeps them in one process)
+        const char *e;
+        a.staged_norm_min_words = (e = getenv("SA_STAGED_NORM_MIN_WORDS")) ? (u32)atol(e) : SA_STAGED_NORM_MIN_WORDS;
+        a.staged_norm_min_recs = (e = getenv("SA_STAGED_NORM_MIN_RECS")) ? (u32)atol(e) : SA_STAGED_NORM_MIN_RECS;
+        a.quad_min_recs = (e = getenv("SA_TERM_QUAD_MIN_RECS")) ? (u32)atol(e) : SA_TERM_QUAD_MIN_RECS;
+        a.prefetch_tiles = (e = getenv("SA_TERM_PREFETCH_TILES")) ? (u32)atol(e) : SA_TERM_PREFETCH_TILES;
+        a.quad_min_recs = std::max(a.quad_min_recs, a.staged_norm_min_recs);   // the quad path reads norms from the staged tile only
     }
     a.tile_dir = ix->d_tile_dir;
     a.recs = (a.words == ix->d_words) ? ix->d_recs : nullptr;     // the tf table describes the index's own lists only

@@ -6,7 +6,9 @@
 #define SA_TERM_UNROLL 4           // 30-word windows loaded per warp before processing
 #define SA_TERM_THREADS 256
 #define SA_STAGED_NORM_MIN_WORDS 1024   // tiles with at least this many posting words stage the tile's norms (sa_term.cu)
-#define SA_STAGED_NORM_MIN_RECS 768     // ... or this many (doc, tf) records on the tf-table path
+#define SA_STAGED_NORM_MIN_RECS 48      // ... or this many (doc, tf) records on the tf-table path
+#define SA_TERM_PREFETCH_TILES 8         // L2 prefetch distance of the tf-table path, in tiles (sa_term.cu)
+#define SA_TERM_QUAD_MIN_RECS 512       // four records per thread from this many records per tile on (and >= 16 * k, sa_term.cu)
 #define SA_TOPK_MAX 32             // warp-level threshold estimation handles k <= 32
 
 enum TermMode { TERM_MODE_TF = 0, TERM_MODE_SCORE = 1 };
@@ -40,6 +42,8 @@ struct TermBatchArgs {
     int filter;                 // apply the payload_slice filter
     int mode;
     u32 staged_norm_min_words;  // set by launch_term_batch
+    u32 staged_norm_min_recs, quad_min_recs;   // set by launch_term_batch
+    u32 prefetch_tiles;         // L2 prefetch distance in tiles on the tf-table path (0 = off); set by launch_term_batch
     u32 query_major;            // grid layout (set by launch_term_batch): 1 = (tiles, queries), 0 = (queries, tiles)
     TopkCtx topk;
 };
