@@ -44,7 +44,7 @@ def main():
                 st.append((float(d[k] or 0), s))
         print("stalled warps per issue-active cycle: " + ", ".join(f"{s} {v:.2f}" for v, s in sorted(st, reverse=True)[:6]))
     src = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], stderr=subprocess.DEVNULL).decode()
-    srows = list(csv.reader(io.StringIO(src)))[2:]
+    srows = [r for r in csv.reader(io.StringIO(src)) if r and r[0].startswith("0x")]     # every launch repeats two header rows
     tmp = "/tmp/ncu_summary_cub"
     subprocess.call(["rm", "-rf", tmp])
     os.makedirs(tmp)
