@@ -545,6 +545,7 @@ def bench_ours(args, rank, world):
     traffic, traffic_src = committed_traffic("term_tile_kernel", {"n_docs": args.docs, "queries_per_step": Q, "n_gpus": world})
     roofline = {"bound": "hbm", "kernel": "term_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0,      # both denominators
                 "algorithmic_bytes_per_launch": float(alg_q.sum()) / launches_per_step,
                 "algorithmic_bytes": "postings + 4*df (norms) + 4*N (dense row) per query (SURVEY 8d), summed over the "
                                      "launch's queries; postings = 4*df for lists scanned through the upload-time "
